@@ -1,0 +1,199 @@
+// Single-operation entry points on HOST buffers (each replaces one reference function; the parity tests call these)
+// and the FP64 peak microbenchmark used as the tensor-roofline denominator.
+#include <vector>
+
+#include "gemm_f64.cuh"
+#include "kernels.cuh"
+#include "linalg.cuh"
+
+using namespace gpirt;
+
+namespace {
+
+struct DevBuf {
+    double* p = nullptr;
+    int alloc(size_t count) {
+        cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(double));
+        if (e != cudaSuccess) { set_last_error("cudaMalloc: %s", cudaGetErrorString(e)); return GPIRT_B200_ERR_NOMEM; }
+        return GPIRT_B200_OK;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+int have_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        set_last_error("no CUDA device available (this library has no CPU fallback)");
+        return GPIRT_B200_ERR_CUDA;
+    }
+    return GPIRT_B200_OK;
+}
+
+int h2d(double* dst, int64_t ld, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+    if (rows == 0 || cols == 0) return GPIRT_B200_OK;
+    GP_CUDA(cudaMemcpy2D(dst, ld * sizeof(double), src, lds * sizeof(double), rows * sizeof(double), cols, cudaMemcpyHostToDevice));
+    return GPIRT_B200_OK;
+}
+int d2h(double* dst, int64_t ldd, const double* src, int64_t ld, int64_t rows, int64_t cols) {
+    if (rows == 0 || cols == 0) return GPIRT_B200_OK;
+    GP_CUDA(cudaMemcpy2D(dst, ldd * sizeof(double), src, ld * sizeof(double), rows * sizeof(double), cols, cudaMemcpyDeviceToHost));
+    return GPIRT_B200_OK;
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void k_peak_dmma(double* out, int iters, double seed) {
+    double c[8][2];
+    const double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = i; c[i][1] = -i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_peak_dfma(double* out, int iters, double seed) {
+    double c[8];
+    const double a = 1.0 + seed * 1e-9, b = seed * 1e-3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = i + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpirt_b200_se_cov(const double* x1, int64_t n1, const double* x2, int64_t n2, double jitter, double* out) {
+    if (!x1 || !x2 || !out || n1 < 0 || n2 < 0) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    if (n1 == 0 || n2 == 0) return GPIRT_B200_OK;
+    const int64_t ld = round_up(n1, 8);
+    DevBuf a, b, o;
+    GP_TRY(a.alloc(n1)); GP_TRY(b.alloc(n2)); GP_TRY(o.alloc(ld * n2));
+    GP_CUDA(cudaMemcpy(a.p, x1, n1 * sizeof(double), cudaMemcpyHostToDevice));
+    GP_CUDA(cudaMemcpy(b.p, x2, n2 * sizeof(double), cudaMemcpyHostToDevice));
+    GP_TRY(launch_se_cov(0, a.p, (int)n1, b.p, (int)n2, jitter, false, o.p, ld));
+    GP_CUDA(cudaDeviceSynchronize());
+    return d2h(out, n1, o.p, ld, n1, n2);
+}
+
+int gpirt_b200_chol_lower(double* S, int64_t n) {
+    if (!S || n < 0) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    if (n == 0) return GPIRT_B200_OK;
+    const int64_t ld = round_up(n, 8);
+    DevBuf a, dinv;
+    int* st = nullptr;
+    GP_TRY(a.alloc(ld * n)); GP_TRY(dinv.alloc(ld * DIAG_NB));
+    GP_CUDA(cudaMalloc((void**)&st, sizeof(int)));
+    GP_CUDA(cudaMemset(st, 0, sizeof(int)));
+    GP_TRY(h2d(a.p, ld, S, n, n, n));
+    int rc = potrf_lower(0, a.p, ld, (int)n, dinv.p, ld, st);
+    int h = 0;
+    if (rc == GPIRT_B200_OK && cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GPIRT_B200_ERR_CUDA;
+    cudaFree(st);
+    if (rc) return rc;
+    if (h) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
+    GP_TRY(d2h(S, n, a.p, ld, n, n));
+    for (int64_t j = 1; j < n; ++j)      // strict upper := 0, as arma::chol(.,"lower")
+        for (int64_t i = 0; i < j; ++i) S[i + j * n] = 0.0;
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                     const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    const int64_t ar = ta ? K : M, ac = ta ? M : K, br = tb ? N : K, bc = tb ? K : N;
+    DevBuf a, b, c;
+    GP_TRY(a.alloc(lda * ac)); GP_TRY(b.alloc(ldb * bc)); GP_TRY(c.alloc(ldc * N));
+    GP_TRY(h2d(a.p, lda, A, lda, ar, ac)); GP_TRY(h2d(b.p, ldb, B, ldb, br, bc)); GP_TRY(h2d(c.p, ldc, C, ldc, M, N));
+    GemmArgs g;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K; g.A = a.p; g.lda = lda; g.B = b.p; g.ldb = ldb; g.C = c.p; g.ldc = ldc;
+    g.alpha = alpha; g.beta = beta; g.tri = tri; g.b_abs = 0;
+    GP_TRY(gemm_f64(0, ta != 0, tb != 0, g));
+    GP_CUDA(cudaDeviceSynchronize());
+    return d2h(C, ldc, c.p, ldc, M, N);
+}
+
+int gpirt_b200_trsm_lower(int trans, int64_t n, int64_t nrhs, const double* L, double* B) {
+    if (!L || !B || n < 0 || nrhs < 0) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    if (n == 0 || nrhs == 0) return GPIRT_B200_OK;
+    const int64_t ld = round_up(n, 8);
+    DevBuf l, dinv, b;
+    GP_TRY(l.alloc(ld * n)); GP_TRY(dinv.alloc(ld * DIAG_NB)); GP_TRY(b.alloc(ld * nrhs));
+    GP_TRY(h2d(l.p, ld, L, n, n, n)); GP_TRY(h2d(b.p, ld, B, n, n, nrhs));
+    GP_TRY(trtri_diag_blocks(0, l.p, ld, (int)n, dinv.p, ld));   // inverses of L's 64 x 64 diagonal blocks
+    GP_TRY(trsm_left_lower(0, trans != 0, (int)n, (int)nrhs, l.p, ld, dinv.p, ld, b.p, ld));
+    GP_CUDA(cudaDeviceSynchronize());
+    return d2h(B, n, b.p, ld, n, nrhs);
+}
+
+int gpirt_b200_ll_bar(const double* f, const double* y, const double* mu, int64_t n, int64_t m, double* out) {
+    if (!f || !y || !mu || !out || n < 0 || m < 0) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    if (m == 0) return GPIRT_B200_OK;
+    DevBuf df, dy, dm, o;
+    GP_TRY(df.alloc(n * m)); GP_TRY(dy.alloc(n * m)); GP_TRY(dm.alloc(n * m)); GP_TRY(o.alloc(m));
+    GP_CUDA(cudaMemcpy(df.p, f, n * m * sizeof(double), cudaMemcpyHostToDevice));
+    GP_CUDA(cudaMemcpy(dy.p, y, n * m * sizeof(double), cudaMemcpyHostToDevice));
+    GP_CUDA(cudaMemcpy(dm.p, mu, n * m * sizeof(double), cudaMemcpyHostToDevice));
+    GP_TRY(launch_ll_bar(0, df.p, dy.p, dm.p, (int)n, (int)m, o.p));
+    GP_CUDA(cudaMemcpy(out, o.p, m * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_fp64_peak_tflops(double* dmma_tflops, double* dfma_tflops) {
+    GP_TRY(have_device());
+    cudaDeviceProp p;
+    GP_CUDA(cudaGetDeviceProperties(&p, 0));
+    int dev = 0;
+    GP_CUDA(cudaGetDevice(&dev));
+    GP_CUDA(cudaGetDeviceProperties(&p, dev));
+    const int sms = p.multiProcessorCount, threads = 256, blocks = sms * 2, iters = 20000;
+    DevBuf o;
+    GP_TRY(o.alloc((size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    GP_CUDA(cudaEventCreate(&e0)); GP_CUDA(cudaEventCreate(&e1));
+    float best_m = 1e30f, best_f = 1e30f, t;
+    for (int r = 0; r < 4; ++r) {
+        GP_CUDA(cudaEventRecord(e0)); GP_LAUNCH(k_peak_dmma, blocks, threads, 0, 0, o.p, iters, 1.0); GP_CUDA(cudaEventRecord(e1));
+        GP_CUDA(cudaEventSynchronize(e1)); GP_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (r && t < best_m) best_m = t;
+        GP_CUDA(cudaEventRecord(e0)); GP_LAUNCH(k_peak_dfma, blocks, threads, 0, 0, o.p, iters, 1.0); GP_CUDA(cudaEventRecord(e1));
+        GP_CUDA(cudaEventSynchronize(e1)); GP_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (r && t < best_f) best_f = t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (dmma_tflops) *dmma_tflops = (double)blocks * (threads / 32) * iters * 8 * 512.0 / best_m * 1e-9;
+    if (dfma_tflops) *dfma_tflops = (double)blocks * threads * (double)iters * 8 * 2.0 / best_f * 1e-9;
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_rng_probe(uint64_t seed, uint32_t sweep, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
+                         double* uniforms, double* normals) {
+    if (count < 0 || !uniforms || !normals) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    if (count == 0) return GPIRT_B200_OK;
+    DevBuf u, z;
+    GP_TRY(u.alloc(count)); GP_TRY(z.alloc(count));
+    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), sweep};
+    GP_TRY(launch_rng_probe(0, key, purpose, stream, idx0, count, u.p, z.p));
+    GP_CUDA(cudaMemcpy(uniforms, u.p, count * sizeof(double), cudaMemcpyDeviceToHost));
+    GP_CUDA(cudaMemcpy(normals, z.p, count * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPIRT_B200_OK;
+}
+
+}  // extern "C"

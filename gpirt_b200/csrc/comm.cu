@@ -1,0 +1,79 @@
+#include "comm.cuh"
+
+#include <dlfcn.h>
+#include <cstring>
+
+namespace gpirt {
+
+namespace {
+// the few NCCL entry points we need, bound at run time (ABI-stable across NCCL 2.x)
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef int (*fn_get_uid)(ncclUniqueId_t*);
+typedef int (*fn_init_rank)(void** comm, int nranks, ncclUniqueId_t id, int rank);
+typedef int (*fn_allreduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t s);
+typedef int (*fn_destroy)(void* comm);
+typedef const char* (*fn_errstr)(int);
+
+struct Api {
+    void* handle = nullptr;
+    fn_get_uid get_uid = nullptr; fn_init_rank init_rank = nullptr; fn_allreduce allreduce = nullptr;
+    fn_destroy destroy = nullptr; fn_errstr errstr = nullptr;
+    bool tried = false;
+} api;
+
+int load_api() {
+    if (api.handle) return GPIRT_B200_OK;
+    if (!api.tried) {
+        api.tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+        if (api.handle) {
+            api.get_uid = (fn_get_uid)dlsym(api.handle, "ncclGetUniqueId");
+            api.init_rank = (fn_init_rank)dlsym(api.handle, "ncclCommInitRank");
+            api.allreduce = (fn_allreduce)dlsym(api.handle, "ncclAllReduce");
+            api.destroy = (fn_destroy)dlsym(api.handle, "ncclCommDestroy");
+            api.errstr = (fn_errstr)dlsym(api.handle, "ncclGetErrorString");
+            if (!api.get_uid || !api.init_rank || !api.allreduce || !api.destroy) { dlclose(api.handle); api.handle = nullptr; }
+        }
+    }
+    if (!api.handle) { set_last_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror()); return GPIRT_B200_ERR_NCCL; }
+    return GPIRT_B200_OK;
+}
+
+int check(int rc, const char* what) {
+    if (rc == 0) return GPIRT_B200_OK;
+    set_last_error("%s failed: %s", what, api.errstr ? api.errstr(rc) : "nccl error");
+    return GPIRT_B200_ERR_NCCL;
+}
+}  // namespace
+
+int comm_unique_id(void* out128) {
+    GP_TRY(load_api());
+    ncclUniqueId_t id;
+    GP_TRY(check(api.get_uid(&id), "ncclGetUniqueId"));
+    std::memcpy(out128, &id, sizeof(id));
+    return GPIRT_B200_OK;
+}
+
+int comm_init(Comm& c, int rank, int world, const void* unique_id128) {
+    c.rank = rank; c.world = world;
+    if (world <= 1) return GPIRT_B200_OK;
+    if (!unique_id128) { set_last_error("world_size > 1 needs opts.nccl_unique_id"); return GPIRT_B200_ERR_ARG; }
+    GP_TRY(load_api());
+    ncclUniqueId_t id;
+    std::memcpy(&id, unique_id128, sizeof(id));
+    return check(api.init_rank(&c.nccl_comm, world, id, rank), "ncclCommInitRank");
+}
+
+int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t stream) {
+    if (c.world <= 1) return GPIRT_B200_OK;
+    const int ncclFloat64 = 8, ncclSum = 0;
+    return check(api.allreduce(buf, buf, count, ncclFloat64, ncclSum, c.nccl_comm, stream), "ncclAllReduce");
+}
+
+void comm_destroy(Comm& c) {
+    if (c.nccl_comm && api.destroy) api.destroy(c.nccl_comm);
+    c.nccl_comm = nullptr;
+}
+
+}  // namespace gpirt

@@ -1,0 +1,18 @@
+// NCCL plumbing for item sharding (one process per GPU).  libnccl is opened lazily with dlopen so that a single-GPU
+// run has no NCCL dependency at all; only the logP all-reduce of the theta step goes through it.
+#pragma once
+#include "common.cuh"
+
+namespace gpirt {
+
+struct Comm {
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+int comm_unique_id(void* out128);
+int comm_init(Comm& c, int rank, int world, const void* unique_id128);
+int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t stream);
+void comm_destroy(Comm& c);
+
+}  // namespace gpirt

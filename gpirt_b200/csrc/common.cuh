@@ -1,0 +1,72 @@
+// Shared host/device helpers for the gpirt_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+
+#include "../../include/gpirt_b200.h"
+
+namespace gpirt {
+
+constexpr int N_GRID = GPIRT_B200_N_GRID;
+
+void set_last_error(const char* fmt, ...);
+
+#define GP_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ::gpirt::set_last_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                                    cudaGetErrorString(e__));                                      \
+            return GPIRT_B200_ERR_CUDA;                                                            \
+        }                                                                                          \
+    } while (0)
+
+#define GP_TRY(call)                                                                               \
+    do {                                                                                           \
+        int rc__ = (call);                                                                         \
+        if (rc__ != GPIRT_B200_OK) return rc__;                                                    \
+    } while (0)
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// launch counter (gpu_launches in bench.py): every kernel launch in this library goes through GP_LAUNCH
+extern int64_t g_launch_count;
+#define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+    do {                                                                                           \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
+        ++::gpirt::g_launch_count;                                                                 \
+    } while (0)
+
+// ---- warp / block reductions (fixed order => deterministic) ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum over the whole block; every thread gets the same value.  `buf` = 32 doubles of shared memory that no other
+// phase is touching between the two barriers (callers alternate between two buffers to save a barrier).
+__device__ __forceinline__ double block_sum(double v, double* buf) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) buf[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += buf[i];
+    return t;
+}
+
+// The reference's per-observation log-likelihood term, src/log-likelihood.cpp:19-20 / :33-34:
+//   result -= log(1 + exp(-a)),  a = y * g          (literal form: overflows to -inf for a < -709, like the reference)
+__device__ __forceinline__ double ll_term(double a) { return log(1.0 + exp(-a)); }
+
+} // namespace gpirt

@@ -1,0 +1,187 @@
+// FP64 GEMM on the Blackwell FP64 tensor pipe (DMMA.8x8x4 via mma.sync.m8n8k4.f64 — tcgen05 has no FP64 kind).
+//
+//   C[M x N] = alpha * op(A)[M x K] * op(B)[K x N] + beta * C          (column-major everywhere)
+//
+// One kernel serves every dense product on the hot path:
+//   nu = L Z                       (draw-f.cpp:26 / mvnormal.h:10, all m items at once)       NN, tri = A lower
+//   blocked triangular solves      (draw-fstar.cpp:7,19)                                        NN / TN updates
+//   mean = (S^-1 K*)^T F           (draw-fstar.cpp:25)                                          TN
+//   logP^T = 1/2 F* Y^T - D |Y|^T  (draw-theta.cpp:18 in contraction form)                      NT
+//   Cholesky trailing updates      (gpirtMCMC.cpp:17,78,97)                                     NT, tri = C lower
+//
+// Tiling: CTA tile BM x BN, k-tile 16, 4-stage cp.async ring in shared memory; each warp owns a
+// (BM/WARPS_M) x (BN/WARPS_N) sub-tile as 8x8 DMMA accumulator fragments held in registers.
+// Shared tiles are padded by 4 doubles so that the 8x4 / 4x8 fragment gathers (lane = 4*g + t reads (g, t)) touch
+// 16 distinct 8-byte words per half-warp: conflict-free for both M/N-contiguous and K-contiguous operands.
+// Loads are 8-byte cp.async with zero-fill predication, so any leading dimension / offset / ragged edge is legal.
+#pragma once
+#include "common.cuh"
+
+namespace gpirt {
+
+enum GemmTri : int {
+    TRI_NONE = 0,
+    TRI_A_LOWER = 1,  // op(A)(m,k) == 0 for k > m : k-tiles beyond the row block are skipped
+    TRI_C_LOWER = 2,  // only C(row >= col) is written (symmetric rank-k update of a lower-stored matrix)
+    TRI_A_UPPER = 3   // op(A)(m,k) == 0 for k < m : k-tiles before the row block are skipped
+};
+
+struct GemmArgs {
+    int M, N, K;
+    const double* A; int64_t lda;
+    const double* B; int64_t ldb;
+    double* C; int64_t ldc;
+    double alpha, beta;
+    int tri;
+    int b_abs;  // use |op(B)| (observed-mask operand of the theta contraction)
+};
+
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_PAD = 4;
+
+__device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* gmem_src, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = pred ? 8 : 0;  // src-size 0 => destination zero-filled, source not read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int BM, int BN>
+constexpr size_t gemm_smem_bytes() {
+    return (size_t)GEMM_STAGES * (size_t)(BM + BN) * (GEMM_BK + GEMM_PAD) * sizeof(double);
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(const GemmArgs g) {
+    constexpr int THREADS = WARPS_M * WARPS_N * 32;
+    constexpr int BK = GEMM_BK, PAD = GEMM_PAD, STAGES = GEMM_STAGES;
+    constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
+    constexpr int MI = WTM / 8, NI = WTN / 8;
+    constexpr int A_STAGE = BM * (BK + PAD), B_STAGE = BN * (BK + PAD);  // doubles (upper bound for both layouts)
+    constexpr int LDA_S = TA ? (BK + PAD) : (BM + PAD);  // TA: As[m][k] ; else As[k][m]
+    constexpr int LDB_S = TB ? (BN + PAD) : (BK + PAD);  // TB: Bs[k][n] ; else Bs[n][k]
+    static_assert((BK * BM) % THREADS == 0 && (BK * BN) % THREADS == 0, "tile/threads mismatch");
+    static_assert(BK * (BM + PAD) <= A_STAGE && BK * (BN + PAD) <= B_STAGE, "stage size");
+
+    extern __shared__ double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+
+    const int mtiles = (g.M + BM - 1) / BM;
+    const int mt = (g.tri == TRI_A_LOWER) ? (mtiles - 1 - (int)blockIdx.x) : (int)blockIdx.x;  // heaviest rows first
+    const int m0 = mt * BM, n0 = (int)blockIdx.y * BN;
+    if (g.tri == TRI_C_LOWER && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
+
+    int k_begin = 0, k_end = g.K;
+    if (g.tri == TRI_A_LOWER) k_end = min(g.K, m0 + BM);
+    if (g.tri == TRI_A_UPPER) k_begin = (m0 / BK) * BK;
+    const int nkt = (k_end - k_begin + BK - 1) / BK;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm0 = (warp % WARPS_M) * WTM, wn0 = (warp / WARPS_M) * WTN;
+
+    auto load_tile = [&](int stage, int kt) {
+        const int k0 = k_begin + kt * BK;
+        double* as = As + stage * A_STAGE;
+        double* bs = Bs + stage * B_STAGE;
+#pragma unroll
+        for (int r = 0; r < (BK * BM) / THREADS; ++r) {
+            const int e = tid + r * THREADS;
+            int m, k;
+            if (TA) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+            const bool ok = (m0 + m < g.M) && (k0 + k < k_end);
+            const double* src = ok ? (TA ? g.A + (int64_t)(k0 + k) + (int64_t)(m0 + m) * g.lda
+                                         : g.A + (int64_t)(m0 + m) + (int64_t)(k0 + k) * g.lda)
+                                   : g.A;
+            cp_async_f64(TA ? as + m * LDA_S + k : as + k * LDA_S + m, src, ok);
+        }
+#pragma unroll
+        for (int r = 0; r < (BK * BN) / THREADS; ++r) {
+            const int e = tid + r * THREADS;
+            int n, k;
+            if (TB) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
+            const bool ok = (n0 + n < g.N) && (k0 + k < k_end);
+            const double* src = ok ? (TB ? g.B + (int64_t)(n0 + n) + (int64_t)(k0 + k) * g.ldb
+                                         : g.B + (int64_t)(k0 + k) + (int64_t)(n0 + n) * g.ldb)
+                                   : g.B;
+            cp_async_f64(TB ? bs + k * LDB_S + n : bs + n * LDB_S + k, src, ok);
+        }
+    };
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nkt) load_tile(s, s);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nkt; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = it + STAGES - 1;
+        if (nxt < nkt) load_tile(nxt % STAGES, nxt);
+        cp_async_commit();
+        const double* as = As + (it % STAGES) * A_STAGE;
+        const double* bs = Bs + (it % STAGES) * B_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[MI], b[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                const int m = wm0 + i * 8 + gq, k = kk + tq;
+                double v = TA ? as[m * LDA_S + k] : as[k * LDA_S + m];
+                a[i] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const int n = wn0 + j * 8 + gq, k = kk + tq;
+                double w = TB ? bs[k * LDB_S + n] : bs[n * LDB_S + k];
+                b[j] = g.b_abs ? fabs(w) : w;
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C fragment (row = g, cols = 2t, 2t+1)
+    const bool has_beta = (g.beta != 0.0);
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm0 + i * 8 + gq;
+        if (row >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = n0 + wn0 + j * 8 + 2 * tq + h;
+                if (col >= g.N) continue;
+                if (g.tri == TRI_C_LOWER && col > row) continue;
+                double* dst = g.C + (int64_t)row + (int64_t)col * g.ldc;
+                double v = g.alpha * acc[i][j][h];
+                if (has_beta) v += g.beta * (*dst);
+                *dst = v;
+            }
+        }
+    }
+}
+
+// host side (gemm.cu)
+int gemm_f64(cudaStream_t stream, bool ta, bool tb, const GemmArgs& g);
+
+}  // namespace gpirt

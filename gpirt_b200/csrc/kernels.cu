@@ -1,0 +1,579 @@
+// Non-GEMM kernels of the Gibbs sweep: covariance builder, response ingest, Philox fills, the batched elliptical
+// slice sampler with the fused logistic log-likelihood, f* finishing draw, theta grid sampler, beta Metropolis step.
+#include "kernels.cuh"
+
+namespace gpirt {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Squared-exponential covariance, reference src/covariance-function.cpp:3-14 (+ S.diag() += 0.001, gpirtMCMC.cpp:16).
+// HBM-write-bound: each thread owns two consecutive rows (one 16-byte store) and walks 8 columns re-using x1.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SE_COLS = 8;
+__global__ void __launch_bounds__(128) k_se_cov(const double* __restrict__ x1, int n1, const double* __restrict__ x2,
+                                                int n2, double jitter, int lower_only, double* __restrict__ out,
+                                                int64_t ld) {
+    const int i0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n1) return;
+    const bool two = (i0 + 1 < n1);
+    const double a0 = x1[i0], a1 = two ? x1[i0 + 1] : 0.0;
+    const int j0 = blockIdx.y * SE_COLS;
+#pragma unroll
+    for (int jj = 0; jj < SE_COLS; ++jj) {
+        const int j = j0 + jj;
+        if (j >= n2) break;
+        const double b = x2[j];
+        double v0 = 0.0, v1 = 0.0;
+        if (!lower_only || i0 >= j) { const double d = a0 - b; v0 = exp(-0.5 * d * d); if (i0 == j) v0 += jitter; }
+        if (two && (!lower_only || i0 + 1 >= j)) { const double d = a1 - b; v1 = exp(-0.5 * d * d); if (i0 + 1 == j) v1 += jitter; }
+        double* dst = out + i0 + (int64_t)j * ld;
+        if (two) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);  // ld even, i0 even => 16-byte aligned
+        else *dst = v0;
+    }
+}
+
+int launch_se_cov(cudaStream_t st, const double* x1, int n1, const double* x2, int n2, double jitter, bool lower_only,
+                  double* out, int64_t ld) {
+    if (n1 <= 0 || n2 <= 0) return GPIRT_B200_OK;
+    if (ld % 2) { set_last_error("se_cov: leading dimension must be even"); return GPIRT_B200_ERR_ARG; }
+    dim3 grid((unsigned)ceil_div(ceil_div(n1, 2), 128), (unsigned)ceil_div(n2, SE_COLS));
+    GP_LAUNCH(k_se_cov, grid, 128, 0, st, x1, n1, x2, n2, jitter, lower_only ? 1 : 0, out, ld);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// theta*_k = start + (k * delta) with two roundings, exactly arma::regspace (gpirtMCMC.cpp:35); prior = dnorm(.,0,1,log)
+__global__ void k_grid_init(double* theta_star, double* prior) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N_GRID) return;
+    const double t = __dadd_rn(-5.0, __dmul_rn((double)k, 0.01));
+    theta_star[k] = t;
+    const double a = fabs(t);
+    prior[k] = -(0.918938533204672741780329736406 + __dmul_rn(__dmul_rn(0.5, a), a) + log(1.0));
+}
+int launch_grid_init(cudaStream_t st, double* theta_star, double* prior) {
+    GP_LAUNCH(k_grid_init, (unsigned)ceil_div(N_GRID, 256), 256, 0, st, theta_star, prior);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// Response ingest (contract: R/response_matrix.R:79-98 produces REALSXP {1,-1,NA_real_}; log-likelihood.cpp:16,30 tests isnan)
+__global__ void k_ingest_y(const double* __restrict__ y, int n, int m, int8_t* __restrict__ y8, int64_t ldy8,
+                           double* __restrict__ yd, int64_t ldyd, unsigned long long* n_missing,
+                           unsigned long long* n_bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= n) return;
+    const double v = y[i + (int64_t)j * n];
+    int8_t c = 0;
+    if (v == 1.0) c = 1;
+    else if (v == -1.0) c = -1;
+    else if (isnan(v)) atomicAdd(n_missing, 1ull);
+    else atomicAdd(n_bad, 1ull);
+    y8[i + (int64_t)j * ldy8] = c;
+    yd[i + (int64_t)j * ldyd] = (double)c;
+}
+int launch_ingest_y(cudaStream_t st, const double* y, int n, int m, int8_t* y8, int64_t ldy8, double* yd, int64_t ldyd,
+                    unsigned long long* n_missing, unsigned long long* n_bad) {
+    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)m);
+    GP_LAUNCH(k_ingest_y, grid, 256, 0, st, y, n, m, y8, ldy8, yd, ldyd, n_missing, n_bad);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Philox fills
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fill_normal(double* __restrict__ Z, int n, int64_t ld, RngKey key,
+                                                     uint32_t purpose, uint32_t item_offset) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int i0 = 2 * pair;
+    if (i0 >= n) return;
+    double za, zb;
+    rng_normal_pair(key, purpose, item_offset + (uint32_t)j, (uint32_t)pair, za, zb);
+    double* dst = Z + i0 + (int64_t)j * ld;
+    if (i0 + 1 < n) *reinterpret_cast<double2*>(dst) = make_double2(za, zb);
+    else *dst = za;
+}
+int launch_fill_normal(cudaStream_t st, double* Z, int n, int m, int64_t ld, RngKey key, uint32_t purpose,
+                       uint32_t item_offset) {
+    if (n <= 0 || m <= 0) return GPIRT_B200_OK;
+    dim3 grid((unsigned)ceil_div(ceil_div(n, 2), 256), (unsigned)m);
+    GP_LAUNCH(k_fill_normal, grid, 256, 0, st, Z, n, ld, key, purpose, item_offset);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+__global__ void k_init_beta(double* beta, const double* pm, const double* psd, int m, RngKey key, uint32_t item_offset) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double z0, z1;
+    rng_normal_pair(key, P_INIT_BETA, item_offset + (uint32_t)j, 0u, z0, z1);
+    beta[2 * j] = __dadd_rn(pm[2 * j], __dmul_rn(psd[2 * j], z0));          // R::rnorm(mu, sigma) = mu + sigma * z
+    beta[2 * j + 1] = __dadd_rn(pm[2 * j + 1], __dmul_rn(psd[2 * j + 1], z1));
+}
+int launch_init_beta(cudaStream_t st, double* beta, const double* pm, const double* psd, int m, RngKey key,
+                     uint32_t item_offset) {
+    GP_LAUNCH(k_init_beta, (unsigned)ceil_div(m, 128), 128, 0, st, beta, pm, psd, m, key, item_offset);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+__global__ void k_rng_probe(RngKey key, uint32_t purpose, uint32_t stream, uint32_t idx0, int count, double* u, double* z) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    u[t] = rng_uniform(key, purpose, stream, idx0 + t);
+    z[t] = rng_normal(key, purpose, stream, idx0 + t);
+}
+int launch_rng_probe(cudaStream_t st, RngKey key, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
+                     double* uniforms, double* normals) {
+    GP_LAUNCH(k_rng_probe, (unsigned)ceil_div(count, 128), 128, 0, st, key, purpose, stream, idx0, count, uniforms, normals);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Elliptical slice sampler, one CTA per item (reference src/draw-f.cpp:21-60, likelihood src/log-likelihood.cpp:25-37).
+// The item's f, nu, y and the linear mean mu_i = beta0 + beta1 theta_i stay in registers (EPT values per thread) for
+// the whole data-dependent shrink loop, so HBM is touched once on the way in and once on the way out.  The block-wide
+// log-likelihood sum is a fixed-order shuffle + shared-memory reduction (every thread ends with the same bits, so the
+// accept test needs no broadcast); the uniforms come from Philox by address, recomputed by every thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int ESS_ITER_CAP = 10000;
+
+template <int EPT>
+__global__ void __launch_bounds__(512) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
+                      int64_t ldy, const double* __restrict__ theta, const double* __restrict__ beta, int n, RngKey key,
+                      uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status) {
+    __shared__ double red[2][32];
+    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const uint32_t item = item_offset + (uint32_t)j;
+    const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
+    double fv[EPT], nv[EPT], gm[EPT], yv[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * T;
+        if (i < n) {
+            fv[e] = f[i + (int64_t)j * ld];
+            nv[e] = nu[i + (int64_t)j * ld];
+            yv[e] = (double)y8[i + (int64_t)j * ldy];
+            gm[e] = fma(theta[i], b1, b0);
+        } else { fv[e] = nv[e] = gm[e] = yv[e] = 0.0; }
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+        if (yv[e] != 0.0) part -= ll_term(yv[e] * (fv[e] + gm[e]));
+    const double ll_cur = block_sum(part, red[0]);
+    const double u = rng_uniform(key, P_ESS_U, item, 0u);
+    const double log_y = ll_cur + log(u);                                            // draw-f.cpp:28-29
+    const double TWO_PI = 6.283185307179586476925286766559;
+    double eps_min = 0.0, eps_max = TWO_PI;                                          // :33-34
+    double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u); // :35 R::runif(a,b) = a + (b-a) u
+    eps_min = eps - TWO_PI;                                                          // :36 (eps_max stays 2 pi)
+    int iter = 0;
+    double s, c;
+    for (;;) {
+        iter += 1;
+        sincos(eps, &s, &c);
+        part = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+            if (yv[e] != 0.0) {
+                const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
+                part -= ll_term(yv[e] * (fp + gm[e]));
+            }
+        const double ll_new = block_sum(part, red[iter & 1]);
+        if (ll_new > log_y) break;                                                   // :45 strict
+        if (eps < 0.0) eps_min = eps; else eps_max = eps;                            // :50-55
+        eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);  // :56
+        if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }    // NaN likelihood: reference would spin
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * T;
+        if (i < n) f[i + (int64_t)j * ld] = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));
+    }
+    if (tid == 0 && nprop) nprop[j] = iter;
+}
+
+// Large-n variant (n > 4096: the item no longer fits the register file of one CTA): same algorithm, but every
+// proposal re-streams f, nu, y, theta from L2 (the 17n bytes of an item stay L2-resident across its shrink loop).
+__global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, const double* __restrict__ nu, int64_t ld,
+                                                     const int8_t* __restrict__ y8, int64_t ldy,
+                                                     const double* __restrict__ theta, const double* __restrict__ beta,
+                                                     int n, RngKey key, uint32_t item_offset, int* __restrict__ nprop,
+                                                     int* __restrict__ status) {
+    __shared__ double red[2][32];
+    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const uint32_t item = item_offset + (uint32_t)j;
+    const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
+    double* fj = f + (int64_t)j * ld;
+    const double* nj = nu + (int64_t)j * ld;
+    const int8_t* yj = y8 + (int64_t)j * ldy;
+    double part = 0.0;
+    for (int i = tid; i < n; i += T) {
+        const double yv = (double)yj[i];
+        if (yv != 0.0) part -= ll_term(yv * (fj[i] + fma(theta[i], b1, b0)));
+    }
+    const double ll_cur = block_sum(part, red[0]);
+    const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));
+    const double TWO_PI = 6.283185307179586476925286766559;
+    double eps_min = 0.0, eps_max = TWO_PI;
+    double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u);
+    eps_min = eps - TWO_PI;
+    int iter = 0;
+    double s, c;
+    for (;;) {
+        iter += 1;
+        sincos(eps, &s, &c);
+        part = 0.0;
+        for (int i = tid; i < n; i += T) {
+            const double yv = (double)yj[i];
+            if (yv != 0.0) {
+                const double fp = __dadd_rn(__dmul_rn(fj[i], c), __dmul_rn(nj[i], s));
+                part -= ll_term(yv * (fp + fma(theta[i], b1, b0)));
+            }
+        }
+        const double ll_new = block_sum(part, red[iter & 1]);
+        if (ll_new > log_y) break;
+        if (eps < 0.0) eps_min = eps; else eps_max = eps;
+        eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);
+        if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }
+    }
+    for (int i = tid; i < n; i += T) fj[i] = __dadd_rn(__dmul_rn(fj[i], c), __dmul_rn(nj[i], s));
+    if (tid == 0 && nprop) nprop[j] = iter;
+}
+
+// block size / elements-per-thread for a per-item CTA holding n <= 4096 respondents in registers (ept = 0: stream)
+static void item_cta_shape(int n, int& ept, int& threads) {
+    if (n <= 256) ept = 1; else if (n <= 1024) ept = 2; else if (n <= 2048) ept = 4; else if (n <= 4096) ept = 8; else ept = 0;
+    threads = ept ? (int)round_up(ceil_div(n, ept), 32) : 1024;
+    if (threads < 32) threads = 32;
+}
+
+int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const int8_t* y8, int64_t ldy,
+               const double* theta, const double* beta, int n, int m, RngKey key, uint32_t item_offset, int* nprop,
+               int* status) {
+    if (m <= 0) return GPIRT_B200_OK;
+    int ept, threads;
+    item_cta_shape(n, ept, threads);
+    switch (ept) {
+        case 1: GP_LAUNCH(k_ess<1>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
+        case 2: GP_LAUNCH(k_ess<2>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
+        case 4: GP_LAUNCH(k_ess<4>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
+        case 8: GP_LAUNCH(k_ess<8>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
+        default: GP_LAUNCH(k_ess_stream, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
+    }
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// f* pieces (reference src/draw-fstar.cpp:19-28)
+// ------------------------------------------------------------------------------------------------------------------
+// s_k = 1 - sqrt(sum_i tmp_ik^2)   (:20 — note 1 - sqrt(.), not sqrt(1 - .)); one warp per grid point
+__global__ void __launch_bounds__(256) k_fstar_sd(const double* __restrict__ tmp, int64_t ld, int n, int N, double* s) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= N) return;
+    const double* col = tmp + (int64_t)k * ld;
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) { const double t = col[i]; acc += t * t; }
+    acc = warp_sum(acc);
+    if (lane == 0) s[k] = 1.0 - sqrt(acc);
+}
+int launch_fstar_sd(cudaStream_t st, const double* tmp, int64_t ld, int n, int N, double* s) {
+    GP_LAUNCH(k_fstar_sd, (unsigned)ceil_div(N, 8), 256, 0, st, tmp, ld, n, N, s);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// f*_kj = rnorm(mean_kj + mu*_kj, s_k), k ascending within item j (:25-28); mu*_kj = beta0_j + beta1_j theta*_k
+__global__ void __launch_bounds__(256) k_fstar_finish(double* __restrict__ fstar, int64_t ld, int N, const double* __restrict__ s,
+                                                      const double* __restrict__ beta, const double* __restrict__ theta_star,
+                                                      RngKey key, uint32_t item_offset, double* __restrict__ irf_sum,
+                                                      int accumulate) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int k0 = 2 * pair;
+    if (k0 >= N) return;
+    double za, zb;
+    rng_normal_pair(key, P_FSTAR_Z, item_offset + (uint32_t)j, (uint32_t)pair, za, zb);
+    const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
+    const int64_t off = k0 + (int64_t)j * ld;
+    {
+        const double mean = fstar[off] + fma(theta_star[k0], b1, b0);
+        const double v = __dadd_rn(mean, __dmul_rn(s[k0], za));
+        fstar[off] = v;
+        if (accumulate) irf_sum[off] += v;
+    }
+    if (k0 + 1 < N) {
+        const double mean = fstar[off + 1] + fma(theta_star[k0 + 1], b1, b0);
+        const double v = __dadd_rn(mean, __dmul_rn(s[k0 + 1], zb));
+        fstar[off + 1] = v;
+        if (accumulate) irf_sum[off + 1] += v;
+    }
+}
+int launch_fstar_finish(cudaStream_t st, double* fstar, int64_t ld, int N, int m, const double* s, const double* beta,
+                        const double* theta_star, RngKey key, uint32_t item_offset, double* irf_sum, int accumulate) {
+    if (m <= 0) return GPIRT_B200_OK;
+    dim3 grid((unsigned)ceil_div(ceil_div(N, 2), 256), (unsigned)m);
+    GP_LAUNCH(k_fstar_finish, grid, 256, 0, st, fstar, ld, N, s, beta, theta_star, key, item_offset, irf_sum, accumulate);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+__global__ void k_irf_finish(const double* __restrict__ irf_sum, int64_t ld, int N, double inv_samples, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (k >= N) return;
+    const double x = irf_sum[k + (int64_t)j * ld] * inv_samples;                   // gpirtMCMC.cpp:106
+    out[k + (int64_t)j * N] = 1.0 / (1.0 + exp(-x));                               // R::plogis, :109
+}
+int launch_irf_finish(cudaStream_t st, const double* irf_sum, int64_t ld, int N, int m, double inv_samples, double* out) {
+    if (m <= 0) return GPIRT_B200_OK;
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)m);
+    GP_LAUNCH(k_irf_finish, grid, 256, 0, st, irf_sum, ld, N, inv_samples, out);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// theta step (reference src/draw-theta.cpp).  The O(n N m) loop of exp+log pairs becomes a contraction:
+//   -log(1+exp(-y f)) = y f / 2 - D(f),  D(f) = log(2 cosh(f/2))   for y = +-1
+//   logP_ik = prior_k + 1/2 sum_j y_ij f*_kj - sum_j obs_ij D_kj
+// k_theta_prep evaluates D once per (k, j) (N m transcendentals instead of n N m) and its row sums.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_theta_prep(const double* __restrict__ fstar, double* __restrict__ D, int64_t ld,
+                                                    int N, int m, double* __restrict__ partial, int n_chunks) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, chunk = blockIdx.y;
+    if (k >= N) return;
+    const int per = (int)ceil_div(m, n_chunks), j0 = chunk * per, j1 = min(m, j0 + per);
+    double acc = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const double v = fstar[k + (int64_t)j * ld];
+        const double a = fabs(v);
+        const double d = 0.5 * a + log1p(exp(-a));
+        D[k + (int64_t)j * ld] = d;
+        acc += d;
+    }
+    partial[(int64_t)chunk * N + k] = acc;
+}
+__global__ void k_reduce_partials(const double* __restrict__ partial, int N, int n_chunks, double* __restrict__ rowsum) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double acc = 0.0;
+    for (int c = 0; c < n_chunks; ++c) acc += partial[(int64_t)c * N + k];
+    rowsum[k] = acc;
+}
+int launch_theta_prep(cudaStream_t st, const double* fstar, double* D, int64_t ld, int N, int m, double* partial,
+                      int n_chunks, double* rowsum) {
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)n_chunks);
+    GP_LAUNCH(k_theta_prep, grid, 128, 0, st, fstar, D, ld, N, m, partial, n_chunks);
+    GP_LAUNCH(k_reduce_partials, (unsigned)ceil_div(N, 128), 128, 0, st, partial, N, n_chunks, rowsum);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// One CTA (256 threads x 4 consecutive grid points) per respondent: P = exp(logP - max), inclusive scan,
+// (P - P_0) / (P_last - P_0) > u  -> first such grid index  (draw-theta.cpp:21-34).
+constexpr int TH_THREADS = 256, TH_EPT = 4;
+static_assert(TH_THREADS * TH_EPT >= N_GRID, "theta draw CTA must cover the grid");
+__global__ void __launch_bounds__(TH_THREADS) k_theta_draw(const double* __restrict__ logPt, int64_t ld,
+                                                           const double* __restrict__ rowsum, const double* __restrict__ prior,
+                                                           const double* __restrict__ theta_star, int N, RngKey key,
+                                                           double* __restrict__ theta, int* __restrict__ idx_out,
+                                                           int* __restrict__ n_degenerate) {
+    __shared__ double red[32];
+    __shared__ double s_first;
+    __shared__ int s_idx[32];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double* col = logPt + (int64_t)i * ld;
+    double v[TH_EPT];
+    double mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < TH_EPT; ++e) {
+        const int k = tid * TH_EPT + e;
+        v[e] = (k < N) ? prior[k] + (col[k] - (rowsum ? rowsum[k] : 0.0)) : -INFINITY;
+        mx = fmax(mx, v[e]);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int q = 1; q < TH_THREADS / 32; ++q) mx = fmax(mx, red[q]);
+    __syncthreads();
+    // local inclusive cumsum
+    double run = 0.0;
+#pragma unroll
+    for (int e = 0; e < TH_EPT; ++e) {
+        const int k = tid * TH_EPT + e;
+        const double p = (k < N) ? exp(v[e] - mx) : 0.0;
+        run += p;
+        v[e] = run;
+    }
+    // exclusive scan of thread totals: warp scan then warp totals
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) red[w] = incl;
+    if (tid == 0) s_first = v[0];
+    __syncthreads();
+    double woff = 0.0, total = 0.0;
+    for (int q = 0; q < TH_THREADS / 32; ++q) { if (q < w) woff += red[q]; total += red[q]; }
+    const double offset = woff + (incl - run);
+    const double p_min = s_first, denom = total - p_min;                              // cumsum is monotone: min = first, max = last
+    const double u = rng_uniform(key, P_THETA_U, (uint32_t)i, 0u);
+    int best = 0x7fffffff;
+#pragma unroll
+    for (int e = TH_EPT - 1; e >= 0; --e) {
+        const int k = tid * TH_EPT + e;
+        const double cdf = ((offset + v[e]) - p_min) / denom;
+        if (k < N && cdf > u) best = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) s_idx[w] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 1; q < TH_THREADS / 32; ++q) best = min(best, s_idx[q]);
+        if (best == 0x7fffffff) {  // degenerate CDF (all mass on grid point 0 => 0/0): the reference reads out of bounds here
+            best = 0;
+            atomicAdd(n_degenerate, 1);
+        }
+        theta[i] = theta_star[best];
+        if (idx_out) idx_out[i] = best;
+    }
+}
+int launch_theta_draw(cudaStream_t st, const double* logPt, int64_t ld, const double* rowsum_or_null,
+                      const double* prior, const double* theta_star, int n, int N, RngKey key, double* theta,
+                      int* idx, int* n_degenerate) {
+    GP_LAUNCH(k_theta_draw, (unsigned)n, TH_THREADS, 0, st, logPt, ld, rowsum_or_null, prior, theta_star, N, key, theta,
+              idx, n_degenerate);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// beta Metropolis step, one CTA per item (reference src/draw-beta.cpp:16-38)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dnorm_log(double x, double mu, double sd) {  // R::dnorm(x, mu, sd, log = 1)
+    const double t = fabs((x - mu) / sd);
+    return -(0.918938533204672741780329736406 + 0.5 * t * t + log(sd));
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(512) k_beta(double* __restrict__ beta, const double* __restrict__ f, int64_t ld, const int8_t* __restrict__ y8,
+                       int64_t ldy, const double* __restrict__ theta, const double* __restrict__ pm,
+                       const double* __restrict__ psd, const double* __restrict__ pstep, int n, RngKey key,
+                       uint32_t item_offset) {
+    __shared__ double red[4][32];
+    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const uint32_t item = item_offset + (uint32_t)j;
+    double fv[EPT], th[EPT], yv[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * T;
+        if (i < n) { fv[e] = f[i + (int64_t)j * ld]; th[e] = theta[i]; yv[e] = (double)y8[i + (int64_t)j * ldy]; }
+        else { fv[e] = th[e] = yv[e] = 0.0; }
+    }
+    double cv[2] = {beta[2 * j], beta[2 * j + 1]};
+    double pv[2] = {cv[0], cv[1]};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
+        pv[k] = __dadd_rn(cv[k], __dmul_rn(pstep[2 * j + k], z));                   // :22
+        const double pv_prior = dnorm_log(pv[k], pm[2 * j + k], psd[2 * j + k]);    // :25
+        const double cv_prior = dnorm_log(cv[k], pm[2 * j + k], psd[2 * j + k]);    // :26
+        double part_p = 0.0, part_c = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+            if (yv[e] != 0.0) {
+                part_p -= ll_term(yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27  ll_bar(rho, y, X * pv)
+                part_c -= ll_term(yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));      // :28  ll_bar(rho, y, X * cv)
+            }
+        const double pv_ll = block_sum(part_p, red[2 * k]);
+        const double cv_ll = block_sum(part_c, red[2 * k + 1]);
+        const double r = pv_prior + pv_ll - cv_prior - cv_ll;                       // :29
+        const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
+        if (log(u) < r) cv[k] = pv[k]; else pv[k] = cv[k];                          // :30-35
+    }
+    if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
+}
+
+__global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta, const double* __restrict__ f, int64_t ld,
+                                                      const int8_t* __restrict__ y8, int64_t ldy,
+                                                      const double* __restrict__ theta, const double* __restrict__ pm,
+                                                      const double* __restrict__ psd, const double* __restrict__ pstep,
+                                                      int n, RngKey key, uint32_t item_offset) {
+    __shared__ double red[4][32];
+    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const uint32_t item = item_offset + (uint32_t)j;
+    const double* fj = f + (int64_t)j * ld;
+    const int8_t* yj = y8 + (int64_t)j * ldy;
+    double cv[2] = {beta[2 * j], beta[2 * j + 1]};
+    double pv[2] = {cv[0], cv[1]};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
+        pv[k] = __dadd_rn(cv[k], __dmul_rn(pstep[2 * j + k], z));
+        const double pv_prior = dnorm_log(pv[k], pm[2 * j + k], psd[2 * j + k]);
+        const double cv_prior = dnorm_log(cv[k], pm[2 * j + k], psd[2 * j + k]);
+        double part_p = 0.0, part_c = 0.0;
+        for (int i = tid; i < n; i += T) {
+            const double yv = (double)yj[i];
+            if (yv != 0.0) {
+                const double fi = fj[i], ti = theta[i];
+                part_p -= ll_term(yv * (fi + fma(ti, pv[1], pv[0])));
+                part_c -= ll_term(yv * (fi + fma(ti, cv[1], cv[0])));
+            }
+        }
+        const double pv_ll = block_sum(part_p, red[2 * k]);
+        const double cv_ll = block_sum(part_c, red[2 * k + 1]);
+        const double r = pv_prior + pv_ll - cv_prior - cv_ll;
+        const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
+        if (log(u) < r) cv[k] = pv[k]; else pv[k] = cv[k];
+    }
+    if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
+}
+
+int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, const int8_t* y8, int64_t ldy,
+                const double* theta, const double* pm, const double* psd, const double* pstep, int n, int m,
+                RngKey key, uint32_t item_offset, int* status) {
+    (void)status;
+    if (m <= 0) return GPIRT_B200_OK;
+    int ept, threads;
+    item_cta_shape(n, ept, threads);
+    switch (ept) {
+        case 1: GP_LAUNCH(k_beta<1>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
+        case 2: GP_LAUNCH(k_beta<2>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
+        case 4: GP_LAUNCH(k_beta<4>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
+        case 8: GP_LAUNCH(k_beta<8>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
+        default: GP_LAUNCH(k_beta_stream, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
+    }
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+// ll_bar per column with explicit mu and double y (host-API helper mirroring log-likelihood.cpp:25-37)
+__global__ void __launch_bounds__(256) k_ll_bar(const double* __restrict__ f, const double* __restrict__ y,
+                                                const double* __restrict__ mu, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int j = blockIdx.x;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double yi = y[i + (int64_t)j * n];
+        if (isnan(yi)) continue;
+        const double g = f[i + (int64_t)j * n] + mu[i + (int64_t)j * n];
+        part -= ll_term(yi * g);
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) out[j] = tot;
+}
+int launch_ll_bar(cudaStream_t st, const double* f, const double* y, const double* mu, int n, int m, double* out) {
+    if (m <= 0) return GPIRT_B200_OK;
+    GP_LAUNCH(k_ll_bar, (unsigned)m, 256, 0, st, f, y, mu, n, out);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+}  // namespace gpirt

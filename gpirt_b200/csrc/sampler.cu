@@ -1,0 +1,543 @@
+// The resident GP-IRT Gibbs sampler: device state + one sweep = the reference's loop body
+// (src/gpirtMCMC.cpp:68-78 / :87-97) as a fixed sequence of kernel launches on one stream, and gpirt_b200_mcmc(),
+// the drop-in for gpirtMCMC() (src/gpirtMCMC.cpp:5-117).
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "comm.cuh"
+#include "gemm_f64.cuh"
+#include "kernels.cuh"
+#include "linalg.cuh"
+
+namespace gpirt {
+
+int64_t g_launch_count = 0;
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap); va_end(ap);
+}
+const char* last_error() { return g_last_error; }
+
+}  // namespace gpirt
+
+using namespace gpirt;
+
+struct gpirt_b200_sampler {
+    int n = 0, m = 0;
+    int64_t ldn = 0, ldN = 0;       // leading dimensions (rounded up to 8 doubles) of n-row and 1001-row matrices
+    gpirt_b200_opts opts{};
+    RngKey key{};
+    uint32_t item_offset = 0;
+    Comm comm;
+    cudaStream_t stream = nullptr;
+    bool has_missing = false;
+    bool timing = true;
+    uint32_t sweep_counter = 0;
+    int64_t launches_at_create = 0;
+
+    int8_t* y8 = nullptr; int64_t ldy8 = 0;
+    double *yd = nullptr, *theta = nullptr, *theta_star = nullptr, *prior = nullptr, *beta = nullptr, *pm = nullptr,
+           *psd = nullptr, *pstep = nullptr, *L = nullptr, *Dinv = nullptr, *f = nullptr, *Z = nullptr, *nu = nullptr,
+           *fstar = nullptr, *Dmat = nullptr, *irf_sum = nullptr, *kstar = nullptr, *s = nullptr, *logPt = nullptr,
+           *partial = nullptr;
+    int *nprop = nullptr, *theta_idx = nullptr, *status = nullptr;  // status[0] chol, [1] ess, [2] theta-degenerate count
+    unsigned long long* counters = nullptr;                        // [0] missing cells, [1] illegal cells
+    static constexpr int N_CHUNKS = 32;
+
+    // ---- timers ----
+    struct Seg { int timer; cudaEvent_t a, b; };
+    std::vector<Seg> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[GPIRT_B200_TIMER_COUNT] = {0};
+    int64_t calls[GPIRT_B200_TIMER_COUNT] = {0};
+    Seg cur{};
+
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void tic(int timer) {
+        if (!timing) return;
+        cur.timer = timer; cur.a = get_event(); cur.b = get_event();
+        cudaEventRecord(cur.a, stream);
+    }
+    void toc() {
+        if (!timing) return;
+        cudaEventRecord(cur.b, stream);
+        pending.push_back(cur);
+    }
+    void flush_timers() {  // call after the stream has been synchronised
+        for (auto& sg : pending) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, sg.a, sg.b) == cudaSuccess) { ms[sg.timer] += t; calls[sg.timer] += 1; }
+            pool.push_back(sg.a); pool.push_back(sg.b);
+        }
+        pending.clear();
+    }
+
+    RngKey key_at(uint32_t sweep) const { RngKey k = key; k.sweep = sweep; return k; }
+
+    template <typename T> int alloc(T*& p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+        if (e != cudaSuccess) { set_last_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return GPIRT_B200_ERR_NOMEM; }
+        p = (T*)q;
+        return GPIRT_B200_OK;
+    }
+
+    int create(const double* y, int64_t n_, int64_t m_, const double* theta_init, const double* pm_h, const double* psd_h,
+               const double* pstep_h, const gpirt_b200_opts* o);
+    int init_draws();
+    int step_draw_f(uint32_t sweep);
+    int step_draw_fstar(uint32_t sweep, int accumulate);
+    int step_draw_theta(uint32_t sweep);
+    int step_draw_beta(uint32_t sweep);
+    int step_rebuild();
+    int sweep(int accumulate);
+    int check_status();
+    void destroy();
+};
+
+static int upload_padded(double* dst, int64_t ld, const double* src_host, int rows, int cols, cudaStream_t st) {
+    GP_CUDA(cudaMemcpy2DAsync(dst, ld * sizeof(double), src_host, (size_t)rows * sizeof(double), (size_t)rows * sizeof(double),
+                              cols, cudaMemcpyHostToDevice, st));
+    return GPIRT_B200_OK;
+}
+static int download_padded(double* dst_host, const double* src, int64_t ld, int rows, int cols, cudaStream_t st) {
+    GP_CUDA(cudaMemcpy2DAsync(dst_host, (size_t)rows * sizeof(double), src, ld * sizeof(double), (size_t)rows * sizeof(double),
+                              cols, cudaMemcpyDeviceToHost, st));
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const double* theta_init, const double* pm_h,
+                               const double* psd_h, const double* pstep_h, const gpirt_b200_opts* o) {
+    if (!y || !theta_init || !pm_h || !psd_h || !pstep_h || n_ <= 0 || m_ <= 0 || n_ > (1 << 20) || m_ > (1 << 24)) {
+        set_last_error("bad argument: null pointer or n, m out of range");
+        return GPIRT_B200_ERR_ARG;
+    }
+    if (o) opts = *o;
+    n = (int)n_; m = (int)m_;
+    ldn = round_up(n, 8); ldN = round_up(N_GRID, 8); ldy8 = round_up(n, 16);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("no CUDA device available (this library has no CPU fallback)");
+        return GPIRT_B200_ERR_CUDA;
+    }
+    if (o && opts.device >= 0) GP_CUDA(cudaSetDevice(opts.device));
+    key.k0 = (uint32_t)opts.seed; key.k1 = (uint32_t)(opts.seed >> 32); key.sweep = 0;
+    if (opts.world_size > 1) {
+        item_offset = (uint32_t)opts.item_offset;
+        GP_TRY(comm_init(comm, opts.rank, opts.world_size, opts.nccl_unique_id));
+    }
+    launches_at_create = g_launch_count;
+    GP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+    const size_t nm = (size_t)ldn * m, Nm = (size_t)ldN * m;
+    GP_TRY(alloc(y8, (size_t)ldy8 * m)); GP_TRY(alloc(yd, nm));
+    GP_TRY(alloc(theta, (size_t)ldn)); GP_TRY(alloc(theta_star, (size_t)ldN)); GP_TRY(alloc(prior, (size_t)ldN));
+    GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
+    GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * DIAG_NB));
+    GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
+    GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
+    GP_TRY(alloc(kstar, (size_t)ldn * N_GRID)); GP_TRY(alloc(s, (size_t)ldN));
+    GP_TRY(alloc(logPt, (size_t)ldN * (n + 1))); GP_TRY(alloc(partial, (size_t)N_CHUNKS * N_GRID));
+    GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2));
+    GP_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int), stream));
+    GP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream));
+    GP_CUDA(cudaMemsetAsync(irf_sum, 0, Nm * sizeof(double), stream));
+    GP_CUDA(cudaMemsetAsync(y8, 0, (size_t)ldy8 * m, stream));
+    GP_CUDA(cudaMemsetAsync(yd, 0, nm * sizeof(double), stream));
+    GP_CUDA(cudaMemsetAsync(f, 0, nm * sizeof(double), stream));
+    GP_CUDA(cudaMemsetAsync(fstar, 0, Nm * sizeof(double), stream));
+    GP_CUDA(cudaMemsetAsync(logPt, 0, (size_t)ldN * (n + 1) * sizeof(double), stream));
+    GP_CUDA(cudaMemsetAsync(nprop, 0, (size_t)m * sizeof(int), stream));
+    GP_CUDA(cudaMemsetAsync(theta_idx, 0, (size_t)n * sizeof(int), stream));
+
+    // y arrives as R hands it over: REALSXP n x m, {1,-1,NA}; staged through the nu buffer (tight n x m fits in ldn x m)
+    GP_CUDA(cudaMemcpyAsync(nu, y, (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice, stream));
+    GP_TRY(launch_ingest_y(stream, nu, n, m, y8, ldy8, yd, ldn, counters, counters + 1));
+    unsigned long long cnt[2];
+    GP_CUDA(cudaMemcpyAsync(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+    GP_CUDA(cudaMemcpyAsync(theta, theta_init, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    GP_CUDA(cudaMemcpyAsync(pm, pm_h, 2 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+    GP_CUDA(cudaMemcpyAsync(psd, psd_h, 2 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+    GP_CUDA(cudaMemcpyAsync(pstep, pstep_h, 2 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+    GP_TRY(launch_grid_init(stream, theta_star, prior));
+    GP_CUDA(cudaStreamSynchronize(stream));
+    if (cnt[1] != 0) {
+        set_last_error("y holds %llu values that are not +1, -1 or NA", cnt[1]);
+        return GPIRT_B200_ERR_Y_VALUE;
+    }
+    has_missing = cnt[0] != 0;
+    GP_TRY(step_rebuild());                                                         // gpirtMCMC.cpp:15-17
+    GP_CUDA(cudaStreamSynchronize(stream));
+    return check_status();
+}
+
+int gpirt_b200_sampler::check_status() {
+    int h[4];
+    GP_CUDA(cudaMemcpyAsync(h, status, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    GP_CUDA(cudaStreamSynchronize(stream));
+    flush_timers();
+    if (h[0]) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
+    if (h[1]) { set_last_error("elliptical slice sampler did not terminate (NaN log-likelihood?)"); return GPIRT_B200_ERR_ESS; }
+    return GPIRT_B200_OK;
+}
+
+// S = K(theta,theta); S.diag() += 0.001; cholS = chol(S,"lower")                     gpirtMCMC.cpp:76-78
+int gpirt_b200_sampler::step_rebuild() {
+    tic(GPIRT_B200_T_KBUILD);
+    GP_TRY(launch_se_cov(stream, theta, n, theta, n, 0.001, true, L, ldn));
+    toc();
+    tic(GPIRT_B200_T_CHOL);
+    GP_TRY(potrf_lower(stream, L, ldn, n, Dinv, ldn, status));
+    toc();
+    return GPIRT_B200_OK;
+}
+
+static GemmArgs G(int M, int N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                  double alpha, double beta, int tri, int b_abs = 0) {
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.alpha = alpha; g.beta = beta; g.tri = tri; g.b_abs = b_abs;
+    return g;
+}
+
+// f = draw_f(f, y, cholS, mu)                                                       gpirtMCMC.cpp:68, draw-f.cpp:64-73
+int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
+    const RngKey k = key_at(sweep);
+    tic(GPIRT_B200_T_FILL_Z);
+    GP_TRY(launch_fill_normal(stream, Z, n, m, ldn, k, sweep == 0 ? P_INIT_F_Z : P_ESS_Z, item_offset));
+    toc();
+    tic(GPIRT_B200_T_LZ_GEMM);   // nu_j = cholS z_j for all items in one product (mvnormal.h:10)
+    GP_TRY(gemm_f64(stream, false, false, G(n, m, n, L, ldn, Z, ldn, sweep == 0 ? f : nu, ldn, 1.0, 0.0, TRI_A_LOWER)));
+    toc();
+    if (sweep == 0) return GPIRT_B200_OK;   // initial f_j = rmvnorm(cholS), gpirtMCMC.cpp:19-21
+    tic(GPIRT_B200_T_ESS);
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, k, item_offset, nprop, status + 1));
+    toc();
+    return GPIRT_B200_OK;
+}
+
+// f_star = draw_fstar(f, theta, theta_star, cholS, mu_star)                         gpirtMCMC.cpp:69, draw-fstar.cpp:10-31
+int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
+    const RngKey k = key_at(sweep);
+    const int N = N_GRID;
+    tic(GPIRT_B200_T_KSTAR);
+    GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));          // :17
+    toc();
+    tic(GPIRT_B200_T_TRSM);
+    GP_TRY(trsm_left_lower(stream, false, n, N, L, ldn, Dinv, ldn, kstar, ldn));             // :19 tmp = L^-1 K*
+    GP_TRY(launch_fstar_sd(stream, kstar, ldn, n, N, s));                                    // :20
+    if (opts.fstar_mode == 0) {
+        // K*^T L^-T L^-1 f_j = (L^-T tmp)^T f_j : solve once for the 1001 grid columns instead of per item
+        GP_TRY(trsm_left_lower(stream, true, n, N, L, ldn, Dinv, ldn, kstar, ldn));
+        toc();
+        tic(GPIRT_B200_T_FSTAR_GEMM);
+        GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, f, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
+        toc();
+    } else {
+        // literal: alpha_j = L^-T (L^-1 f_j) for every item (:3-8,:24), mean_j = K*^T alpha_j (:25)
+        GP_CUDA(cudaMemcpyAsync(Z, f, (size_t)ldn * m * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        GP_TRY(trsm_left_lower(stream, false, n, m, L, ldn, Dinv, ldn, Z, ldn));
+        GP_TRY(trsm_left_lower(stream, true, n, m, L, ldn, Dinv, ldn, Z, ldn));
+        toc();
+        tic(GPIRT_B200_T_FSTAR_GEMM);
+        GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));
+        GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, Z, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
+        toc();
+    }
+    tic(GPIRT_B200_T_FSTAR_DRAW);
+    GP_CUDA(cudaMemcpyAsync(Dmat, fstar, (size_t)ldN * m * sizeof(double), cudaMemcpyDeviceToDevice, stream));  // keep means for tests
+    GP_TRY(launch_fstar_finish(stream, fstar, ldN, N, m, s, beta, theta_star, k, item_offset, irf_sum, accumulate));  // :26-28
+    toc();
+    return GPIRT_B200_OK;
+}
+
+__global__ void k_sub_rowsum(double* logPt, int64_t ld, int N, int n, const double* rowsum) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (k < N && i < n) logPt[k + (int64_t)i * ld] -= rowsum[k];
+}
+
+// theta = draw_theta(theta_star, y, theta_prior, f_star, mu_star)                   gpirtMCMC.cpp:70, draw-theta.cpp:3-37
+int gpirt_b200_sampler::step_draw_theta(uint32_t sweep) {
+    const RngKey k = key_at(sweep);
+    const int N = N_GRID;
+    double* rowsum = logPt + (size_t)ldN * n;   // column n of the logP buffer (rides along in the all-reduce)
+    tic(GPIRT_B200_T_THETA_PREP);
+    GP_TRY(launch_theta_prep(stream, fstar, Dmat, ldN, N, m, partial, N_CHUNKS, rowsum));
+    toc();
+    tic(GPIRT_B200_T_THETA_GEMM);
+    // logP^T[k,i] = 1/2 sum_j f*_kj y_ij   (y = 0 where missing)
+    GP_TRY(gemm_f64(stream, false, true, G(N, n, m, fstar, ldN, yd, ldn, logPt, ldN, 0.5, 0.0, TRI_NONE)));
+    const double* rs_for_draw = rowsum;
+    if (has_missing) {  // - sum_j obs_ij D_kj with obs = |y|
+        GP_TRY(gemm_f64(stream, false, true, G(N, n, m, Dmat, ldN, yd, ldn, logPt, ldN, -1.0, 1.0, TRI_NONE, 1)));
+        rs_for_draw = nullptr;
+    }
+    toc();
+    if (comm.world > 1) {
+        tic(GPIRT_B200_T_ALLREDUCE);
+        if (!has_missing) {
+            dim3 grid((unsigned)ceil_div(N, 256), (unsigned)n);
+            GP_LAUNCH(k_sub_rowsum, grid, 256, 0, stream, logPt, ldN, N, n, rowsum);
+        }
+        rs_for_draw = nullptr;
+        GP_TRY(comm_allreduce_sum_f64(comm, logPt, (size_t)ldN * n, stream));
+        toc();
+    }
+    tic(GPIRT_B200_T_THETA_DRAW);
+    GP_TRY(launch_theta_draw(stream, logPt, ldN, rs_for_draw, prior, theta_star, n, N, k, theta, theta_idx, status + 2));
+    toc();
+    return GPIRT_B200_OK;
+}
+
+// beta = draw_beta(beta, X, y, f, ...) with X.col(1) = the NEW theta                 gpirtMCMC.cpp:71-73, draw-beta.cpp
+int gpirt_b200_sampler::step_draw_beta(uint32_t sweep) {
+    tic(GPIRT_B200_T_BETA);
+    GP_TRY(launch_beta(stream, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1));
+    toc();
+    return GPIRT_B200_OK;
+}
+
+// initial draws, gpirtMCMC.cpp:18-41 (sweep counter 0): f_j = cholS z_j, beta ~ N(pm, psd), f* = draw_fstar(...)
+int gpirt_b200_sampler::init_draws() {
+    sweep_counter = 0;
+    GP_TRY(step_draw_f(0));
+    GP_TRY(launch_init_beta(stream, beta, pm, psd, m, key_at(0), item_offset));
+    GP_TRY(step_draw_fstar(0, 0));
+    return check_status();
+}
+
+int gpirt_b200_sampler::sweep(int accumulate) {
+    const uint32_t t = ++sweep_counter;
+    GP_TRY(step_draw_f(t));
+    GP_TRY(step_draw_fstar(t, accumulate));
+    GP_TRY(step_draw_theta(t));
+    GP_TRY(step_draw_beta(t));
+    GP_TRY(step_rebuild());   // mu = X beta and mu* = X* beta (gpirtMCMC.cpp:74-75) are never materialised
+    return GPIRT_B200_OK;
+}
+
+void gpirt_b200_sampler::destroy() {
+    if (stream) cudaStreamSynchronize(stream);
+    flush_timers();
+    for (auto e : pool) cudaEventDestroy(e);
+    pool.clear();
+    comm_destroy(comm);
+    void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
+                    kstar, s, logPt, partial, nprop, theta_idx, status, counters};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+}
+
+// ======================================================================================================================
+// C ABI
+// ======================================================================================================================
+extern "C" {
+
+const char* gpirt_b200_strerror(int status) {
+    switch (status) {
+        case GPIRT_B200_OK: return "ok";
+        case GPIRT_B200_ERR_ARG: return "invalid argument";
+        case GPIRT_B200_ERR_CUDA: return "CUDA error (no device or runtime failure)";
+        case GPIRT_B200_ERR_NOT_PD: return "chol(): decomposition failed";
+        case GPIRT_B200_ERR_INTERRUPT: return "interrupted";
+        case GPIRT_B200_ERR_Y_VALUE: return "response matrix holds values other than 1, -1, NA";
+        case GPIRT_B200_ERR_ESS: return "elliptical slice sampler did not terminate";
+        case GPIRT_B200_ERR_NCCL: return "NCCL error";
+        case GPIRT_B200_ERR_NOMEM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+const char* gpirt_b200_last_error(void) { return gpirt::last_error(); }
+
+int gpirt_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int gpirt_b200_nccl_unique_id(void* out128) { return comm_unique_id(out128); }
+
+int gpirt_b200_sampler_create(gpirt_b200_sampler** out, const double* y, int64_t n, int64_t m, const double* theta_init,
+                              const double* pm, const double* psd, const double* pstep, const gpirt_b200_opts* opts) {
+    if (!out) return GPIRT_B200_ERR_ARG;
+    *out = nullptr;
+    gpirt_b200_sampler* s = new gpirt_b200_sampler();
+    int rc = s->create(y, n, m, theta_init, pm, psd, pstep, opts);
+    if (rc != GPIRT_B200_OK) { s->destroy(); delete s; return rc; }
+    *out = s;
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler_init_draws(gpirt_b200_sampler* s) { return s ? s->init_draws() : GPIRT_B200_ERR_ARG; }
+
+int gpirt_b200_sampler_sweep(gpirt_b200_sampler* s, int n_sweeps, int accumulate_irf, float* elapsed_ms) {
+    if (!s || n_sweeps < 0) return GPIRT_B200_ERR_ARG;
+    cudaEvent_t e0, e1;
+    GP_CUDA(cudaEventCreate(&e0)); GP_CUDA(cudaEventCreate(&e1));
+    GP_CUDA(cudaEventRecord(e0, s->stream));
+    int rc = GPIRT_B200_OK;
+    for (int t = 0; t < n_sweeps && rc == GPIRT_B200_OK; ++t) rc = s->sweep(accumulate_irf);
+    GP_CUDA(cudaEventRecord(e1, s->stream));
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { set_last_error("sweep failed: %s", cudaGetErrorString(e)); rc = GPIRT_B200_ERR_CUDA; }
+    if (elapsed_ms && rc == GPIRT_B200_OK) cudaEventElapsedTime(elapsed_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != GPIRT_B200_OK) return rc;
+    return s->check_status();
+}
+
+int gpirt_b200_sampler_step(gpirt_b200_sampler* s, int step, uint32_t sweep) {
+    if (!s) return GPIRT_B200_ERR_ARG;
+    int rc;
+    switch (step) {
+        case GPIRT_B200_STEP_DRAW_F: rc = s->step_draw_f(sweep); break;
+        case GPIRT_B200_STEP_DRAW_FSTAR: rc = s->step_draw_fstar(sweep, 0); break;
+        case GPIRT_B200_STEP_DRAW_THETA: rc = s->step_draw_theta(sweep); break;
+        case GPIRT_B200_STEP_DRAW_BETA: rc = s->step_draw_beta(sweep); break;
+        case GPIRT_B200_STEP_REBUILD: rc = s->step_rebuild(); break;
+        default: return GPIRT_B200_ERR_ARG;
+    }
+    if (rc != GPIRT_B200_OK) return rc;
+    return s->check_status();
+}
+
+static int field_shape(gpirt_b200_sampler* s, int field, double** dev, int64_t* ld, int* rows, int* cols) {
+    const int N = N_GRID;
+    switch (field) {
+        case GPIRT_B200_THETA: *dev = s->theta; *ld = s->ldn; *rows = s->n; *cols = 1; return 0;
+        case GPIRT_B200_BETA: *dev = s->beta; *ld = 2; *rows = 2; *cols = s->m; return 0;
+        case GPIRT_B200_F: *dev = s->f; *ld = s->ldn; *rows = s->n; *cols = s->m; return 0;
+        case GPIRT_B200_FSTAR: *dev = s->fstar; *ld = s->ldN; *rows = N; *cols = s->m; return 0;
+        case GPIRT_B200_CHOL: *dev = s->L; *ld = s->ldn; *rows = s->n; *cols = s->n; return 0;
+        case GPIRT_B200_NU: *dev = s->nu; *ld = s->ldn; *rows = s->n; *cols = s->m; return 0;
+        case GPIRT_B200_FSTAR_S: *dev = s->s; *ld = s->ldN; *rows = N; *cols = 1; return 0;
+        case GPIRT_B200_FSTAR_MEAN: *dev = s->Dmat; *ld = s->ldN; *rows = N; *cols = s->m; return 0;
+        case GPIRT_B200_IRF_SUM: *dev = s->irf_sum; *ld = s->ldN; *rows = N; *cols = s->m; return 0;
+        default: return -1;
+    }
+}
+
+int gpirt_b200_sampler_get(gpirt_b200_sampler* s, int field, double* host_out) {
+    if (!s || !host_out) return GPIRT_B200_ERR_ARG;
+    const int N = N_GRID;
+    if (field == GPIRT_B200_LOGP) {  // n x N, log-likelihood part only (host transposes the device's N x n layout)
+        std::vector<double> t((size_t)N * (s->n + 1));
+        GP_TRY(download_padded(t.data(), s->logPt, s->ldN, N, s->n + 1, s->stream));
+        GP_CUDA(cudaStreamSynchronize(s->stream));
+        const bool sub = !s->has_missing && s->comm.world <= 1;
+        for (int i = 0; i < s->n; ++i)
+            for (int k = 0; k < N; ++k)
+                host_out[(size_t)k * s->n + i] = t[(size_t)i * N + k] - (sub ? t[(size_t)s->n * N + k] : 0.0);
+        return GPIRT_B200_OK;
+    }
+    if (field == GPIRT_B200_THETA_IDX || field == GPIRT_B200_ESS_NPROP) {
+        const int cnt = field == GPIRT_B200_THETA_IDX ? s->n : s->m;
+        std::vector<int> t(cnt);
+        GP_CUDA(cudaMemcpyAsync(t.data(), field == GPIRT_B200_THETA_IDX ? s->theta_idx : s->nprop, cnt * sizeof(int),
+                                cudaMemcpyDeviceToHost, s->stream));
+        GP_CUDA(cudaStreamSynchronize(s->stream));
+        for (int i = 0; i < cnt; ++i) host_out[i] = (double)t[i];
+        return GPIRT_B200_OK;
+    }
+    double* dev; int64_t ld; int rows, cols;
+    if (field_shape(s, field, &dev, &ld, &rows, &cols)) return GPIRT_B200_ERR_ARG;
+    GP_TRY(download_padded(host_out, dev, ld, rows, cols, s->stream));
+    GP_CUDA(cudaStreamSynchronize(s->stream));
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler_set(gpirt_b200_sampler* s, int field, const double* host_in) {
+    if (!s || !host_in) return GPIRT_B200_ERR_ARG;
+    double* dev; int64_t ld; int rows, cols;
+    if (field_shape(s, field, &dev, &ld, &rows, &cols)) return GPIRT_B200_ERR_ARG;
+    GP_TRY(upload_padded(dev, ld, host_in, rows, cols, s->stream));
+    GP_CUDA(cudaStreamSynchronize(s->stream));
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler_timings(gpirt_b200_sampler* s, double* ms, int64_t* calls, int reset) {
+    if (!s) return GPIRT_B200_ERR_ARG;
+    for (int i = 0; i < GPIRT_B200_TIMER_COUNT; ++i) {
+        if (ms) ms[i] = s->ms[i];
+        if (calls) calls[i] = s->calls[i];
+        if (reset) { s->ms[i] = 0.0; s->calls[i] = 0; }
+    }
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled) {
+    if (!s) return GPIRT_B200_ERR_ARG;
+    s->timing = enabled != 0;
+    return GPIRT_B200_OK;
+}
+
+int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s) { return s ? g_launch_count - s->launches_at_create : 0; }
+
+void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s) {
+    if (!s) return;
+    s->destroy();
+    delete s;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// gpirtMCMC(): src/gpirtMCMC.cpp:5-117
+// ----------------------------------------------------------------------------------------------------------------------
+int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_init, int sample_iterations,
+                    int burn_iterations, const double* pm, const double* psd, const double* pstep,
+                    const gpirt_b200_opts* opts, double* theta_out, double* beta_out, double* f_out, double* irf_out,
+                    gpirt_b200_progress_cb cb, void* cb_ctx) {
+    if (sample_iterations < 0 || burn_iterations < 0 || !theta_out || !beta_out || !irf_out) {
+        set_last_error("bad argument: negative iteration count or null output");
+        return GPIRT_B200_ERR_ARG;
+    }
+    const bool keep_f = !(opts && opts->skip_f_draws);
+    if (keep_f && !f_out) { set_last_error("f_out is NULL but f draws were requested"); return GPIRT_B200_ERR_ARG; }
+    gpirt_b200_sampler* s = nullptr;
+    GP_TRY(gpirt_b200_sampler_create(&s, y, n, m, theta_init, pm, psd, pstep, opts));
+    s->timing = false;
+    struct Guard { gpirt_b200_sampler* s; double* pinned; ~Guard() { if (pinned) cudaHostUnregister(pinned); gpirt_b200_sampler_destroy(s); } } guard{s, nullptr};
+    const int S1 = sample_iterations + 1;
+    const size_t nm = (size_t)n * m;
+    std::vector<double> th((size_t)n);
+    // pin the caller's f array so the per-iteration slices go out by DMA at full PCIe rate (best effort)
+    if (keep_f && cudaHostRegister(f_out, nm * S1 * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) guard.pinned = f_out;
+    else cudaGetLastError();
+
+    int rc = s->init_draws();
+    if (rc) return rc;
+    auto store = [&](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
+        GP_CUDA(cudaMemcpyAsync(th.data(), s->theta, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        GP_CUDA(cudaMemcpyAsync(beta_out + (size_t)slot * 2 * m, s->beta, 2 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        if (keep_f) GP_TRY(download_padded(f_out + (size_t)slot * nm, s->f, s->ldn, (int)n, (int)m, s->stream));
+        GP_CUDA(cudaStreamSynchronize(s->stream));
+        for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * S1 + slot] = th[i];
+        return GPIRT_B200_OK;
+    };
+    GP_TRY(store(0));                                                               // :53-55
+    const int total = sample_iterations + burn_iterations;
+    const double inc = total > 0 ? 100.0 / total : 0.0;
+    double progress = 0.0;
+    for (int iter = 0; iter < total; ++iter) {
+        if (cb && cb(progress, cb_ctx)) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
+        progress += inc;
+        const bool sampling = iter >= burn_iterations;
+        GP_TRY(s->sweep(sampling ? 1 : 0));
+        if (sampling) GP_TRY(store(iter - burn_iterations + 1));                    // :99-103
+    }
+    GP_CUDA(cudaStreamSynchronize(s->stream));
+    GP_TRY(s->check_status());
+    // IRFs = plogis(IRFs / S)   (:106-111; S = 0 gives NaN exactly as the reference's 0 * inf)
+    const double inv = 1.0 / (double)sample_iterations;
+    GP_TRY(launch_irf_finish(s->stream, s->irf_sum, s->ldN, N_GRID, (int)m, inv, s->Dmat));
+    GP_CUDA(cudaMemcpyAsync(irf_out, s->Dmat, (size_t)N_GRID * m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    GP_CUDA(cudaStreamSynchronize(s->stream));
+    if (cb) cb(100.0, cb_ctx);
+    return GPIRT_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+"""GPU parity tests (-m gpu): every CUDA step against the CPU oracle on the same seeded inputs and the same addressed
+Philox variates, called through the C ABI (gpirt_b200/_lib.py -> libgpirt_b200.so).
+
+Stated FP64 tolerances (north_star: "within a stated FP64 tolerance given identical injected random draws"):
+  K                      |dK| <= 4e-16 (exp() implementations differ by <= 1-2 ulp of values <= 1)
+  Cholesky factor        |L L^T - S| <= 1e-12 |S|max ; |L - L_oracle| <= 1e-9 (cond(S) up to ~1e7)
+  L z, triangular solves relative 1e-12 / 1e-9 (solves, conditioning)
+  log-likelihoods, logP  relative 1e-12
+  ESS / beta / theta     discrete decisions (accept, shrink count, grid index) identical; values to 1e-9
+"""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from conftest import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpirt_b200.sampler as g
+    from gpirt_b200 import _lib
+    assert _lib.load().gpirt_b200_device_count() > 0, "no CUDA device"
+    return g
+
+
+def test_rng_matches_oracle(G, O):
+    seed = 0x1234ABCD9876
+    for purpose, stream, sweep in [(2, 0, 1), (3, 17, 5), (4, 999, 1000), (5, 4095, 7)]:
+        u, z = G.rng_probe(seed, sweep, purpose, stream, 0, 64)
+        uo = np.array([O.keyed_uniform(seed, sweep, purpose, stream, i) for i in range(64)])
+        zo = np.array([O.keyed_normal(seed, sweep, purpose, stream, i) for i in range(64)])
+        assert np.array_equal(u, uo), "Philox uniforms must be bit-exact"
+        assert np.max(np.abs(z - zo)) <= 2e-15
+    assert (u > 0).all() and (u < 1).all()
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (7, 5), (100, 1001), (257, 257), (1024, 130)])
+def test_se_cov(G, O, n1, n2):
+    rs = np.random.RandomState(n1 + n2)
+    x1, x2 = rs.randn(n1) * 2, rs.randn(n2) * 2
+    got, want = G.se_cov(x1, x2), O.K(x1, x2)
+    assert np.max(np.abs(got - want)) <= 4e-16
+    if n1 == n2:
+        got = G.se_cov(x1, x1, jitter=1e-3)
+        want = O.K(x1, x1) + 1e-3 * np.eye(n1)
+        assert np.max(np.abs(got - want)) <= 4e-16
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (8, 8, 4), (130, 67, 33), (64, 200, 64), (300, 257, 100), (1001, 700, 513),
+                                   (1500, 1400, 260)])
+def test_dgemm(G, ta, tb, M, N, K):
+    rs = np.random.RandomState(M * 7 + N * 3 + K)
+    A = rs.randn(*((K, M) if ta else (M, K)))
+    B = rs.randn(*((N, K) if tb else (K, N)))
+    C0 = rs.randn(M, N)
+    want = 1.5 * (A.T if ta else A) @ (B.T if tb else B) - 0.5 * C0
+    got = G.dgemm(A, B, C0, alpha=1.5, beta=-0.5, ta=ta, tb=tb)
+    scale = np.abs(A).max() * np.abs(B).max() * K + 1
+    assert np.max(np.abs(got - want)) <= 1e-13 * scale
+    got0 = G.dgemm(A, B, None, ta=ta, tb=tb)
+    assert np.max(np.abs(got0 - (A.T if ta else A) @ (B.T if tb else B))) <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("n,m", [(100, 37), (300, 300), (1100, 1300)])
+def test_dgemm_triangular_modes(G, n, m):
+    rs = np.random.RandomState(n)
+    L = np.tril(rs.randn(n, n))
+    Z = rs.randn(n, m)
+    got = G.dgemm(L, Z, None, tri=1)                       # A lower triangular: skipped k-tiles must be exactly the zeros
+    assert np.max(np.abs(got - L @ Z)) <= 1e-12 * n
+    got = G.dgemm(L, Z, None, ta=True, tri=3)              # op(A) = L^T upper triangular
+    assert np.max(np.abs(got - L.T @ Z)) <= 1e-12 * n
+    A = rs.randn(n, 70)
+    C0 = rs.randn(n, n)
+    got = G.dgemm(A, A, C0, alpha=-1.0, beta=1.0, tb=True, tri=2)   # symmetric update, lower triangle only
+    want = C0 - A @ A.T
+    lower = np.tril_indices(n)
+    upper = np.triu_indices(n, 1)
+    assert np.max(np.abs(got[lower] - want[lower])) <= 1e-12 * 70
+    assert np.array_equal(got[upper], C0[upper]), "strict upper triangle must be untouched"
+
+
+@pytest.mark.parametrize("n", [1, 8, 63, 64, 65, 100, 257, 1000, 2048])
+def test_chol_lower(G, O, n):
+    prob = make_problem(n, 2, seed=n, grid_theta=True)     # theta on the 0.01 grid => duplicated rows, PD only by jitter
+    S = O.K(prob["theta"], prob["theta"]) + 1e-3 * np.eye(n)
+    L = G.chol_lower(S)
+    Lo = O.chol_lower(S)
+    assert np.array_equal(np.triu(L, 1), np.zeros_like(L)), "strict upper must be exactly zero"
+    assert np.max(np.abs(L @ L.T - S)) <= 1e-12 * np.abs(S).max() * max(1, np.log2(n + 1))
+    assert np.max(np.abs(L - Lo)) <= 1e-9
+
+
+def test_chol_not_pd(G):
+    from gpirt_b200._lib import GpirtError, ERR_NOT_PD
+    S = np.ones((70, 70))                                  # rank one, no jitter -> chol(): decomposition failed
+    with pytest.raises(GpirtError) as e:
+        G.chol_lower(S)
+    assert e.value.status == ERR_NOT_PD
+
+
+@pytest.mark.parametrize("trans", [False, True])
+@pytest.mark.parametrize("n,r", [(5, 3), (64, 10), (100, 1001), (257, 40), (1000, 300)])
+def test_trsm_lower(G, O, n, r, trans):
+    prob = make_problem(n, 2, seed=n + r, grid_theta=True)
+    L = O.build_cholS(prob["theta"])
+    B = np.random.RandomState(r).randn(n, r)
+    got = G.trsm_lower(L, B, trans=trans)
+    want = sla.solve_triangular(L, B, lower=True, trans="T" if trans else "N")
+    assert np.max(np.abs(got - want)) <= 1e-9 * max(1.0, np.abs(want).max())
+    resid = (L.T if trans else L) @ got - B
+    assert np.max(np.abs(resid)) <= 1e-11 * max(1.0, np.abs(got).max())
+
+
+def test_ll_bar(G, O):
+    prob = make_problem(300, 20, seed=3)
+    rs = np.random.RandomState(1)
+    f = rs.randn(300, 20) * 2; mu = rs.randn(300, 20)
+    got = G.ll_bar(f, prob["y"], mu)
+    want = np.array([O.ll_bar(f[:, j], prob["y"][:, j], mu[:, j]) for j in range(20)])
+    assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# step-level parity through the resident sampler: same state, same addressed variates, one step
+# ---------------------------------------------------------------------------------------------------------------------
+def _state(G, O, n, m, seed, missing, fstar_mode=0):
+    from gpirt_b200 import _lib
+    prob = make_problem(n, m, seed=seed, missing=missing, grid_theta=True)
+    s = G.Sampler(prob["y"], prob["theta"], prob["pm"], prob["psd"], prob["pstep"], seed=seed + 77, fstar_mode=fstar_mode)
+    rs = np.random.RandomState(seed + 1)
+    L = s.get(_lib.CHOL)
+    f = L @ rs.randn(n, m)
+    beta = rs.randn(2, m)
+    s.set(_lib.F, f); s.set(_lib.BETA, beta)
+    return prob, s, L, f, beta
+
+
+@pytest.mark.parametrize("n,m,missing", [(40, 12, 0.1), (100, 50, 0.05), (300, 64, 0.0), (1100, 20, 0.1), (2500, 6, 0.0)])
+def test_step_draw_f(G, O, n, m, missing):
+    from gpirt_b200 import _lib
+    prob, s, L, f, beta = _state(G, O, n, m, seed=n + m, missing=missing)
+    sweep = 3
+    s.step(_lib.STEP_DRAW_F, sweep)
+    nu = s.get(_lib.NU); f_new = s.get(_lib.F); nprop = s.get(_lib.ESS_NPROP).astype(int)
+    rng = O.Rng.keyed(n + m + 77); rng.set_sweep(sweep)
+    mu = O.linear_mean(prob["theta"], beta)
+    fo, npo = O.draw_f(f, prob["y"], L, mu, rng)
+    # proposals nu = L z
+    z = np.array([[O.keyed_normal(n + m + 77, sweep, O.P_ESS_Z, j, i) for j in range(m)] for i in range(n)])
+    assert np.max(np.abs(nu - L @ z)) <= 1e-12 * max(1.0, np.abs(nu).max())
+    assert np.array_equal(nprop, npo), "ESS shrink counts must match the oracle"
+    assert np.max(np.abs(f_new - fo)) <= 1e-9
+    s.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,m,missing", [(40, 12, 0.1), (100, 50, 0.05), (300, 33, 0.0)])
+def test_step_draw_fstar(G, O, n, m, missing, mode):
+    from gpirt_b200 import _lib
+    prob, s, L, f, beta = _state(G, O, n, m, seed=n * 3 + m, missing=missing, fstar_mode=mode)
+    sweep = 2
+    s.step(_lib.STEP_DRAW_FSTAR, sweep)
+    fs = s.get(_lib.FSTAR); sd = s.get(_lib.FSTAR_S); mean = s.get(_lib.FSTAR_MEAN)
+    ts, _ = O.grid()
+    rng = O.Rng.keyed(n * 3 + m + 77); rng.set_sweep(sweep)
+    fso, so, meano = O.draw_fstar(f, prob["theta"], ts, L, O.linear_mean(ts, beta), rng)
+    mu_star = O.linear_mean(ts, beta)
+    assert np.max(np.abs(sd - so)) <= 1e-9
+    assert np.max(np.abs((mean + mu_star) - meano)) <= 1e-8 * max(1.0, np.abs(meano).max())
+    assert np.max(np.abs(fs - fso)) <= 1e-8 * max(1.0, np.abs(fso).max())
+    s.close()
+
+
+@pytest.mark.parametrize("n,m,missing", [(40, 12, 0.1), (100, 50, 0.05), (300, 64, 0.0), (700, 150, 0.3)])
+def test_step_draw_theta(G, O, n, m, missing):
+    from gpirt_b200 import _lib
+    prob, s, L, f, beta = _state(G, O, n, m, seed=n * 5 + m, missing=missing)
+    rs = np.random.RandomState(5)
+    ts, prior = O.grid()
+    fstar = np.asfortranarray(0.8 * rs.randn(1001, m).cumsum(axis=0) * 0.05 + rs.randn(1, m))
+    s.set(_lib.FSTAR, fstar)
+    sweep = 9
+    s.step(_lib.STEP_DRAW_THETA, sweep)
+    th = s.get(_lib.THETA); idx = s.get(_lib.THETA_IDX).astype(int); logp = s.get(_lib.LOGP)
+    rng = O.Rng.keyed(n * 5 + m + 77); rng.set_sweep(sweep)
+    tho, idxo, logpo = O.draw_theta(ts, prob["y"], prior, fstar, rng, mode=1)
+    want_ll = logpo - prior[None, :]
+    assert np.max(np.abs(logp - want_ll) / np.maximum(1.0, np.abs(want_ll))) <= 1e-12
+    assert np.array_equal(idx, idxo), "grid indices must match the oracle (stabilised CDF)"
+    assert np.array_equal(th, tho), "theta values are grid points: bit-exact"
+    s.close()
+
+
+@pytest.mark.parametrize("n,m,missing", [(40, 12, 0.1), (100, 50, 0.05), (1100, 20, 0.0), (2500, 6, 0.1)])
+def test_step_draw_beta(G, O, n, m, missing):
+    from gpirt_b200 import _lib
+    prob, s, L, f, beta = _state(G, O, n, m, seed=n * 7 + m, missing=missing)
+    sweep = 4
+    s.step(_lib.STEP_DRAW_BETA, sweep)
+    b = s.get(_lib.BETA)
+    rng = O.Rng.keyed(n * 7 + m + 77); rng.set_sweep(sweep)
+    bo, acc = O.draw_beta(beta, prob["theta"], prob["y"], f, prob["pm"], prob["psd"], prob["pstep"], rng)
+    assert np.max(np.abs(b - bo)) <= 1e-13
+    assert 0 < acc.sum() < acc.size or m < 8
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# lock-step chains: the whole sampler against the oracle's gpirtMCMC restatement, same seed
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,S,B,mode", [(30, 10, 3, 2, 0), (30, 10, 3, 2, 1), (100, 40, 2, 1, 0), (257, 33, 2, 0, 0)])
+def test_lockstep_chain(G, O, n, m, S, B, mode):
+    prob = make_problem(n, m, seed=n + 11, missing=0.08)
+    seed = 4242 + n
+    from gpirt_b200 import ResponseMatrix
+    got = G.gpirtMCMC(ResponseMatrix(prob["y"]), S, B, beta_prior_means=prob["pm"], beta_prior_sds=prob["psd"],
+                      beta_proposal_sds=prob["pstep"], theta_init=prob["theta"], seed=seed, fstar_mode=mode)
+    rng = O.Rng.keyed(seed)
+    want = O.mcmc(prob["y"], prob["theta"], S, B, prob["pm"], prob["psd"], prob["pstep"], rng, theta_cdf_mode=1)
+    assert got["theta"].shape == (S + 1, n) and got["beta"].shape == (2, m, S + 1)
+    assert got["f"].shape == (n, m, S + 1) and got["IRFs"].shape == (1001, m)
+    assert np.array_equal(got["theta"][0], prob["theta"]), "row 0 holds the initial values (gpirtMCMC.cpp:53)"
+    assert np.array_equal(got["theta"], want["theta"]), "theta draws (grid points) must be identical"
+    assert np.max(np.abs(got["beta"] - want["beta"])) <= 1e-9
+    assert np.max(np.abs(got["f"] - want["f"])) <= 1e-7
+    assert np.max(np.abs(got["IRFs"] - want["IRFs"])) <= 1e-7
+
+
+def test_senate116_short_chain(G, O):
+    import warnings
+    import gpirt_b200
+    codes, _, _ = gpirt_b200.senate116()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        y = gpirt_b200.response_matrix(codes)
+    assert y.shape == (100, 418)
+    theta0 = np.random.RandomState(116).randn(100)
+    got = G.gpirtMCMC(y, 2, 1, theta_init=theta0, seed=116)
+    rng = O.Rng.keyed(116)
+    m = y.shape[1]
+    want = O.mcmc(np.asarray(y), theta0, 2, 1, np.zeros((2, m)), np.full((2, m), 3.0), np.full((2, m), 0.1), rng,
+                  theta_cdf_mode=0)   # strict reference mode is finite on senate116
+    assert np.array_equal(got["theta"], want["theta"])
+    assert np.max(np.abs(got["beta"] - want["beta"])) <= 1e-9
+    assert np.max(np.abs(got["f"] - want["f"])) <= 1e-7
+    assert np.max(np.abs(got["IRFs"] - want["IRFs"])) <= 1e-7
+
+
+def test_interrupt_and_bad_y(G):
+    from gpirt_b200._lib import GpirtError, ERR_INTERRUPT, ERR_Y_VALUE
+    prob = make_problem(20, 6, seed=1)
+    from gpirt_b200 import ResponseMatrix
+    with pytest.raises(GpirtError) as e:
+        G.gpirtMCMC(ResponseMatrix(prob["y"]), 5, 5, theta_init=prob["theta"], seed=1, progress=lambda pct: pct >= 30.0)
+    assert e.value.status == ERR_INTERRUPT
+    bad_raw = np.array(prob["y"]); bad_raw[0, 0] = 6.0
+    s_err = None
+    try:
+        G.Sampler(bad_raw, prob["theta"])
+    except GpirtError as ex:
+        s_err = ex.status
+    assert s_err == ERR_Y_VALUE
