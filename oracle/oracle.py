@@ -263,6 +263,7 @@ def ref():
         L.gpref_ll_bar.restype = C.c_double
         L.gpref_set_tape.argtypes = [_dp, _bp, C.c_size_t]
         L.gpref_tape_pos.restype = C.c_size_t
+        L.gpref_seed.argtypes = [C.c_uint64]
         _ref = L
     return _ref
 
@@ -281,6 +282,7 @@ class RefTape:
     def __exit__(self, *a):
         self.consumed = ref().gpref_tape_pos()
         self.error = ref().gpref_tape_error()
+        ref().gpref_clear_tape()   # back to the self-contained generator (timing runs)
         return False
 
 

@@ -37,8 +37,26 @@ static double tape_pop(uint8_t want) {
     if (g_kinds[g_pos] != want) g_err = 2;
     return g_vals[g_pos++];
 }
-double refshim_norm_rand(void) { return tape_pop('n'); }
-double refshim_unif_rand(void) { return tape_pop('u'); }
+/* With no tape installed (timing runs: bench.py cpu_baseline / --impl reference) a self-contained generator stands in
+ * for R's: xoshiro256** uniforms in (0,1), normals by the Marsaglia polar method. */
+static uint64_t g_s[4] = {0x9E3779B97F4A7C15ull, 0xBF58476D1CE4E5B9ull, 0x94D049BB133111EBull, 0x2545F4914F6CDD1Dull};
+static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static double xo_unif(void) {
+    const uint64_t r = rotl(g_s[1] * 5, 7) * 9, t = g_s[1] << 17;
+    g_s[2] ^= g_s[0]; g_s[3] ^= g_s[1]; g_s[1] ^= g_s[2]; g_s[0] ^= g_s[3]; g_s[2] ^= t; g_s[3] = rotl(g_s[3], 45);
+    return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+static double xo_norm(void) {
+    static int have = 0; static double spare;
+    if (have) { have = 0; return spare; }
+    double u, v, q;
+    do { u = 2.0 * xo_unif() - 1.0; v = 2.0 * xo_unif() - 1.0; q = u * u + v * v; } while (q >= 1.0 || q == 0.0);
+    const double f = std::sqrt(-2.0 * std::log(q) / q);
+    spare = v * f; have = 1;
+    return u * f;
+}
+double refshim_norm_rand(void) { return g_vals ? tape_pop('n') : xo_norm(); }
+double refshim_unif_rand(void) { return g_vals ? tape_pop('u') : xo_unif(); }
 
 static arma::mat M(const double* p, size_t r, size_t c) { return arma::mat(p, r, c); }
 static arma::vec V(const double* p, size_t n) { return arma::vec(arma::mat(p, n, 1)); }
@@ -47,6 +65,8 @@ static void out(const arma::mat& a, double* dst) { std::memcpy(dst, a.memptr(), 
 extern "C" {
 
 void gpref_set_tape(const double* vals, const uint8_t* kinds, size_t len) { g_vals = vals; g_kinds = kinds; g_len = len; g_pos = 0; g_err = 0; }
+void gpref_clear_tape(void) { g_vals = nullptr; g_kinds = nullptr; g_len = g_pos = 0; g_err = 0; }
+void gpref_seed(uint64_t s) { for (int i = 0; i < 4; ++i) { s += 0x9E3779B97F4A7C15ull; uint64_t z = s; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; g_s[i] = z ^ (z >> 31); } }
 size_t gpref_tape_pos(void) { return g_pos; }
 int gpref_tape_error(void) { return g_err; }
 void gpref_set_quiet(int q) { refshim_quiet = q; }
