@@ -246,7 +246,7 @@ def main():
     # roofline of the dominant kernel (largest share of the timed region)
     m_loc = j1 - j0
     work = {"lz_gemm": ("tensor", float(n) * n * m_loc), "fstar_gemm": ("tensor", 2.0 * n * N_GRID * m_loc),
-            "theta_gemm": ("tensor", 2.0 * n * N_GRID * m_loc), "chol": ("tensor", n ** 3 / 3.0),
+            "theta_gemm": ("tensor", 2.0 * n * N_GRID * m_loc), "chol": ("tensor", n ** 3 / 3.0), "trtri": ("tensor", n ** 3 / 3.0),
             "trsm": ("tensor", 2.0 * n * n * N_GRID if args.fstar_mode == 0 else n * n * N_GRID + 2.0 * n * n * m_loc),
             "ess": ("hbm", 25.0 * n * m_loc), "beta": ("hbm", 17.0 * n * m_loc), "kbuild": ("hbm", 4.0 * n * n)}
     tot_ms = sum(v[0] for v in timers.values()) or 1.0

@@ -24,7 +24,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NOT_PD, ERR_INTERRUPT, ERR_Y_VALUE, ERR_ESS, ERR_NCCL
 (THETA, BETA, F, FSTAR, CHOL, LOGP, NU, FSTAR_S, FSTAR_MEAN, IRF_SUM, THETA_IDX, ESS_NPROP) = range(12)
 STEP_DRAW_F, STEP_DRAW_FSTAR, STEP_DRAW_THETA, STEP_DRAW_BETA, STEP_REBUILD = 1, 2, 3, 4, 5
 TIMER_NAMES = ["fill_z", "lz_gemm", "ess", "kstar", "trsm", "fstar_gemm", "fstar_draw", "theta_prep", "theta_gemm",
-               "allreduce", "theta_draw", "beta", "kbuild", "chol"]
+               "allreduce", "theta_draw", "beta", "kbuild", "chol", "trtri"]
 
 
 class GpirtError(RuntimeError):

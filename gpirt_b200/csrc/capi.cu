@@ -97,11 +97,11 @@ int gpirt_b200_chol_lower(double* S, int64_t n) {
     const int64_t ld = round_up(n, 8);
     DevBuf a, dinv;
     int* st = nullptr;
-    GP_TRY(a.alloc(ld * n)); GP_TRY(dinv.alloc(ld * DIAG_NB));
+    GP_TRY(a.alloc(ld * n)); GP_TRY(dinv.alloc(ld * CHOL_NB));
     GP_CUDA(cudaMalloc((void**)&st, sizeof(int)));
     GP_CUDA(cudaMemset(st, 0, sizeof(int)));
     GP_TRY(h2d(a.p, ld, S, n, n, n));
-    int rc = potrf_lower(0, a.p, ld, (int)n, dinv.p, ld, st);
+    int rc = potrf_lower_rl(0, a.p, ld, (int)n, dinv.p, ld, st);
     int h = 0;
     if (rc == GPIRT_B200_OK && cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GPIRT_B200_ERR_CUDA;
     cudaFree(st);
@@ -123,7 +123,7 @@ int gpirt_b200_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alp
     GP_TRY(h2d(a.p, lda, A, lda, ar, ac)); GP_TRY(h2d(b.p, ldb, B, ldb, br, bc)); GP_TRY(h2d(c.p, ldc, C, ldc, M, N));
     GemmArgs g;
     g.M = (int)M; g.N = (int)N; g.K = (int)K; g.A = a.p; g.lda = lda; g.B = b.p; g.ldb = ldb; g.C = c.p; g.ldc = ldc;
-    g.alpha = alpha; g.beta = beta; g.tri = tri; g.b_abs = 0;
+    g.alpha = alpha; g.beta = beta; g.tri = tri;
     GP_TRY(gemm_f64(0, ta != 0, tb != 0, g));
     GP_CUDA(cudaDeviceSynchronize());
     return d2h(C, ldc, c.p, ldc, M, N);

@@ -13,7 +13,7 @@ static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
         GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN));
+    dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)g.batch);
     GP_LAUNCH(kern, grid, dim3(WM * WN * 32), smem, stream, g);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -21,13 +21,13 @@ static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
 
 template <bool TA, bool TB>
 static int launch_layout(cudaStream_t stream, const GemmArgs& g) {
-    const int64_t tiles128 = ceil_div(g.M, 128) * ceil_div(g.N, 128);
-    if (tiles128 >= 112) return launch_cfg<128, 128, 4, 2, TA, TB>(stream, g);
+    const int64_t tiles128 = ceil_div(g.M, 128) * ceil_div(g.N, 128) * g.batch;
+    if (tiles128 >= 112 || g.force_big) return launch_cfg<128, 128, 4, 2, TA, TB>(stream, g);
     return launch_cfg<64, 64, 2, 2, TA, TB>(stream, g);
 }
 
 int gemm_f64(cudaStream_t stream, bool ta, bool tb, const GemmArgs& g) {
-    if (g.M <= 0 || g.N <= 0) return GPIRT_B200_OK;
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return GPIRT_B200_OK;
     if (ta && tb) { set_last_error("gemm_f64: op(A)=T with op(B)=T is not instantiated"); return GPIRT_B200_ERR_ARG; }
     if (ta) return launch_layout<true, false>(stream, g);
     if (tb) return launch_layout<false, true>(stream, g);

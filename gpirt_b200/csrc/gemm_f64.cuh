@@ -23,17 +23,21 @@ enum GemmTri : int {
     TRI_NONE = 0,
     TRI_A_LOWER = 1,  // op(A)(m,k) == 0 for k > m : k-tiles beyond the row block are skipped
     TRI_C_LOWER = 2,  // only C(row >= col) is written (symmetric rank-k update of a lower-stored matrix)
-    TRI_A_UPPER = 3   // op(A)(m,k) == 0 for k < m : k-tiles before the row block are skipped
+    TRI_A_UPPER = 3,  // op(A)(m,k) == 0 for k < m : k-tiles before the row block are skipped
+    TRI_B_LOWER = 4   // op(B)(k,n) == 0 for k < n : k-tiles before the column block are skipped
 };
 
 struct GemmArgs {
-    int M, N, K;
-    const double* A; int64_t lda;
-    const double* B; int64_t ldb;
-    double* C; int64_t ldc;
-    double alpha, beta;
-    int tri;
-    int b_abs;  // use |op(B)| (observed-mask operand of the theta contraction)
+    int M = 0, N = 0, K = 0;
+    const double* A = nullptr; int64_t lda = 0;
+    const double* B = nullptr; int64_t ldb = 0;
+    double* C = nullptr; int64_t ldc = 0;
+    double alpha = 1.0, beta = 0.0;
+    int tri = TRI_NONE;
+    int b_abs = 0;      // use |op(B)| (observed-mask operand of the theta contraction)
+    int batch = 1;      // blockIdx.z indexes independent problems at fixed pointer strides
+    int64_t strideA = 0, strideB = 0, strideC = 0;
+    int force_big = 0;  // always use the 128 x 128 tile (needed when C aliases A or B and N <= 128: one N tile)
 };
 
 constexpr int GEMM_BK = 16;
@@ -75,14 +79,19 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
 
+    // grid: x = column tiles (fastest: neighbouring CTAs share the A row panel in L2), y = row tiles, z = batch
     const int mtiles = (g.M + BM - 1) / BM;
-    const int mt = (g.tri == TRI_A_LOWER) ? (mtiles - 1 - (int)blockIdx.x) : (int)blockIdx.x;  // heaviest rows first
-    const int m0 = mt * BM, n0 = (int)blockIdx.y * BN;
+    const int mt = (g.tri == TRI_A_LOWER) ? (mtiles - 1 - (int)blockIdx.y) : (int)blockIdx.y;  // heaviest rows first
+    const int m0 = mt * BM, n0 = (int)blockIdx.x * BN;
     if (g.tri == TRI_C_LOWER && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
+    const double* __restrict__ gA = g.A + (int64_t)blockIdx.z * g.strideA;
+    const double* __restrict__ gB = g.B + (int64_t)blockIdx.z * g.strideB;
+    double* __restrict__ gC = g.C + (int64_t)blockIdx.z * g.strideC;
 
     int k_begin = 0, k_end = g.K;
     if (g.tri == TRI_A_LOWER) k_end = min(g.K, m0 + BM);
     if (g.tri == TRI_A_UPPER) k_begin = (m0 / BK) * BK;
+    if (g.tri == TRI_B_LOWER) k_begin = (n0 / BK) * BK;
     const int nkt = (k_end - k_begin + BK - 1) / BK;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,9 +108,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
             int m, k;
             if (TA) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
             const bool ok = (m0 + m < g.M) && (k0 + k < k_end);
-            const double* src = ok ? (TA ? g.A + (int64_t)(k0 + k) + (int64_t)(m0 + m) * g.lda
-                                         : g.A + (int64_t)(m0 + m) + (int64_t)(k0 + k) * g.lda)
-                                   : g.A;
+            const double* src = ok ? (TA ? gA + (int64_t)(k0 + k) + (int64_t)(m0 + m) * g.lda
+                                         : gA + (int64_t)(m0 + m) + (int64_t)(k0 + k) * g.lda)
+                                   : gA;
             cp_async_f64(TA ? as + m * LDA_S + k : as + k * LDA_S + m, src, ok);
         }
 #pragma unroll
@@ -110,9 +119,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
             int n, k;
             if (TB) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
             const bool ok = (n0 + n < g.N) && (k0 + k < k_end);
-            const double* src = ok ? (TB ? g.B + (int64_t)(n0 + n) + (int64_t)(k0 + k) * g.ldb
-                                         : g.B + (int64_t)(k0 + k) + (int64_t)(n0 + n) * g.ldb)
-                                   : g.B;
+            const double* src = ok ? (TB ? gB + (int64_t)(n0 + n) + (int64_t)(k0 + k) * g.ldb
+                                         : gB + (int64_t)(k0 + k) + (int64_t)(n0 + n) * g.ldb)
+                                   : gB;
             cp_async_f64(TB ? bs + k * LDB_S + n : bs + n * LDB_S + k, src, ok);
         }
     };
@@ -159,8 +168,30 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
     }
     cp_async_wait<0>();
 
-    // epilogue: C fragment (row = g, cols = 2t, 2t+1)
+    // epilogue: C fragment (row = g, cols = 2t, 2t+1).  Two passes so that, with beta != 0, all loads of the old C are
+    // in flight together instead of being serialised behind the stores (the compiler cannot prove they do not alias).
     const bool has_beta = (g.beta != 0.0);
+    if (has_beta) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int row = m0 + wm0 + i * 8 + gq;
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = n0 + wn0 + j * 8 + 2 * tq + h;
+                    double old = 0.0;
+                    if (row < g.M && col < g.N && !(g.tri == TRI_C_LOWER && col > row))
+                        old = __ldcg(gC + (int64_t)row + (int64_t)col * g.ldc);
+                    acc[i][j][h] = g.alpha * acc[i][j][h] + g.beta * old;
+                }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) { acc[i][j][0] *= g.alpha; acc[i][j][1] *= g.alpha; }
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         const int row = m0 + wm0 + i * 8 + gq;
@@ -172,10 +203,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
                 const int col = n0 + wn0 + j * 8 + 2 * tq + h;
                 if (col >= g.N) continue;
                 if (g.tri == TRI_C_LOWER && col > row) continue;
-                double* dst = g.C + (int64_t)row + (int64_t)col * g.ldc;
-                double v = g.alpha * acc[i][j][h];
-                if (has_beta) v += g.beta * (*dst);
-                *dst = v;
+                gC[(int64_t)row + (int64_t)col * g.ldc] = acc[i][j][h];
             }
         }
     }

@@ -9,6 +9,8 @@
 #include "gemm_f64.cuh"
 #include "linalg.cuh"
 
+#include <algorithm>
+
 namespace gpirt {
 
 // One CTA, 256 threads = 64 rows x 4 k-slices.  Left-looking (Crout) Cholesky of an nb x nb (nb <= 64) lower block
@@ -118,7 +120,7 @@ static GemmArgs mk(int M, int N, int K, const double* A, int64_t lda, const doub
                    int64_t ldc, double alpha, double beta, int tri) {
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
-    g.alpha = alpha; g.beta = beta; g.tri = tri; g.b_abs = 0;
+    g.alpha = alpha; g.beta = beta; g.tri = tri;
     return g;
 }
 
@@ -175,6 +177,334 @@ int trsm_left_lower(cudaStream_t stream, bool trans, int n, int nrhs, const doub
     if (n <= 0 || nrhs <= 0) return GPIRT_B200_OK;
     return trans ? trsm_left_t(stream, n, nrhs, L, ldl, Dinv, ldd, B, ldb)
                  : trsm_left_n(stream, n, nrhs, L, ldl, Dinv, ldd, B, ldb);
+}
+
+// ======================================================================================================================
+// 128 x 128 diagonal block: Cholesky factor AND its inverse in one CTA (512 threads).
+//
+// One shared array S[128][129] holds everything: strictly below the diagonal L, on the diagonal 1/L_rr (= the inverse's
+// diagonal), strictly above the diagonal the transpose of X = L^-1 (X(r,c) lives at S[c][r]); L's own diagonal goes to
+// ldiag[].  Recursion 128 -> 64 -> 32: a 32 x 32 diagonal block is factorised and inverted by ONE warp without block
+// barriers (lane = row for the Crout factorisation, lane = column for the forward substitutions); the off-diagonal
+// work ( L21 = A21 X11^T,  A22 -= L21 L21^T,  X21 = -X22 L21 X11 ) is done by the whole CTA from shared memory.
+// ======================================================================================================================
+namespace {
+constexpr int DB = CHOL_NB, DLD = DB + 1, DTHREADS = 512;
+
+// fast 1/p for p > 0: single-precision seed + two Newton steps (4 dependent DFMAs instead of the full division routine)
+__device__ __forceinline__ double fast_rcp(double p) {
+    double r = (double)__frcp_rn((float)p);
+    r = fma(r, fma(-p, r, 1.0), r);
+    r = fma(r, fma(-p, r, 1.0), r);
+    return r;
+}
+
+// 32 x 32 diagonal block at offset o, all 512 threads, ONE barrier per column, factor and inverse in the same loop.
+// Symmetric Gaussian elimination  A = Lh D Lh^T  (Lh unit lower):  step c uses the unscaled column c and the pivot p_c,
+//   a_ij -= (a_ic / p_c) a_jc                         (i >= j > c)
+//   W_ij -= (a_ic / p_c) W_cj ,  W_ic = -(a_ic / p_c)  (i > c >= j;  W accumulates Lh^-1, W_cc = 1 implicit)
+// and afterwards  L = Lh D^1/2 : l_ij = a_ij / sqrt(p_j),   X = L^-1 = D^-1/2 W : x_ij = W_ij / sqrt(p_i).
+// W_ij lives transposed at S[j][i] (strict upper triangle), pivots in pv[].
+__device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o, int tid, int* status) {
+    const int j = tid & 31, i0 = tid >> 5;   // column j, rows i0 and i0 + 16
+    bool bad = false;
+    for (int c = 0; c < 32; ++c) {
+        const int cc = o + c;
+        const double p = S[cc * DLD + cc];
+        bad |= !(p > 0.0);
+        const double pinv = fast_rcp(p);
+        if (tid == 0) pv[cc] = p;
+        // one predicated path for all lanes (no divergence): j > c updates A(i,j); j <= c updates W(i,j) stored at
+        // S[j][i], where j == c is the fresh column W(i,c) = 0 - mlt * 1 (the strict upper triangle starts as zeros)
+        const double other = (j == c) ? 1.0 : S[(o + j) * DLD + cc];   // a_jc, or W(c,j) which lives at S[o+j][o+c]
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + 16 * u;
+            const double mlt = S[(o + i) * DLD + cc] * pinv;
+            double* tgt = (j > c) ? &S[(o + i) * DLD + o + j] : &S[(o + j) * DLD + o + i];
+            const bool active = (i > c) && (j <= c || i >= j);
+            if (active) *tgt = fma(-mlt, other, *tgt);
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0) atomicExch(status, 1);   // not positive definite (or NaN)
+    // scale: l_ij = a_ij rsqrt(p_j) (i > j);  x_ij = W_ij rsqrt(p_i), stored at S[j][i];  diagonals
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = i0 + 16 * u;
+        if (i > j) {
+            S[(o + i) * DLD + o + j] *= rsqrt(pv[o + j]);
+            S[(o + j) * DLD + o + i] *= rsqrt(pv[o + i]);
+        } else if (i == j) {
+            const double pp = pv[o + i], rs = rsqrt(pp);
+            ldiag[o + i] = pp * rs;
+            S[(o + i) * DLD + o + i] = rs;
+        }
+    }
+    __syncthreads();
+}
+
+// L21 = A21 X11^T, block rows ro.., block cols co.. (H x H), X11 = inverse of the diagonal block at co.
+// Thread -> row i = tid % H and the PER columns j = tid / H + t (DTHREADS / H); the PER dot products advance together
+// (one load of A21(i,k) feeds all of them; PER independent FMA chains hide the FP64 latency).
+template <int H>
+__device__ void mm_panel(double* S, int ro, int co, int tid) {
+    constexpr int PER = (H * H) / DTHREADS, JS = DTHREADS / H;
+    const int i = tid % H, jb = tid / H;
+    const double* a = S + (ro + i) * DLD + co;
+    double acc[PER];
+#pragma unroll
+    for (int t = 0; t < PER; ++t) acc[t] = 0.0;
+    for (int k = 0; k < H; ++k) {                       // X11(j,k) = S[(co+k)][co+j], k <= j
+        const double av = a[k];
+        const double* xr = S + (co + k) * DLD + co;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) {
+            const int j = jb + t * JS;
+            if (k <= j) acc[t] = fma(av, xr[j], acc[t]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < PER; ++t) S[(ro + i) * DLD + co + jb + t * JS] = acc[t];
+    __syncthreads();
+}
+
+// A22 -= L21 L21^T (lower triangle incl. diagonal); A22 at (ro, ro), L21 at (ro, co)
+template <int H>
+__device__ void mm_syrk(double* S, int ro, int co, int tid) {
+    constexpr int PER = (H * H) / DTHREADS, JS = DTHREADS / H;
+    const int i = tid % H, jb = tid / H;
+    const double* a = S + (ro + i) * DLD + co;
+    double acc[PER];
+#pragma unroll
+    for (int t = 0; t < PER; ++t) acc[t] = 0.0;
+    for (int k = 0; k < H; ++k) {
+        const double av = a[k];
+#pragma unroll
+        for (int t = 0; t < PER; ++t) acc[t] = fma(av, S[(ro + jb + t * JS) * DLD + co + k], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+        const int j = jb + t * JS;
+        if (i >= j) S[(ro + i) * DLD + ro + j] -= acc[t];
+    }
+    __syncthreads();
+}
+
+// X21 = -X22 (L21 X11); X21(i,j) is stored at S[co+j][ro+i]
+template <int H>
+__device__ void mm_inv_offdiag(double* S, int ro, int co, int tid) {
+    constexpr int PER = (H * H) / DTHREADS, JS = DTHREADS / H;
+    const int i = tid % H, jb = tid / H;
+    double acc[PER];
+    // T = L21 X11 into the X21 slot:  T(i,j) = sum_{k >= j} L21(i,k) X11(k,j),  X11(k,j) = S[co+j][co+k]
+    {
+        const double* a = S + (ro + i) * DLD + co;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) acc[t] = 0.0;
+        for (int k = 0; k < H; ++k) {
+            const double av = a[k];
+#pragma unroll
+            for (int t = 0; t < PER; ++t) {
+                const int j = jb + t * JS;
+                if (k >= j) acc[t] = fma(av, S[(co + j) * DLD + co + k], acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < PER; ++t) S[(co + jb + t * JS) * DLD + ro + i] = acc[t];
+    }
+    __syncthreads();
+    // X21(i,j) = - sum_{k <= i} X22(i,k) T(k,j),  X22(i,k) = S[ro+k][ro+i],  T(k,j) = S[co+j][ro+k]
+#pragma unroll
+    for (int t = 0; t < PER; ++t) acc[t] = 0.0;
+    for (int k = 0; k <= i; ++k) {
+        const double xv = S[(ro + k) * DLD + ro + i];
+#pragma unroll
+        for (int t = 0; t < PER; ++t) acc[t] = fma(xv, S[(co + jb + t * JS) * DLD + ro + k], acc[t]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < PER; ++t) S[(co + jb + t * JS) * DLD + ro + i] = -acc[t];
+    __syncthreads();
+}
+
+__device__ void factor_invert_64(double* S, double* ldiag, double* pv, int o, int tid, int* status) {
+    diag32_factor_invert(S, ldiag, pv, o, tid, status);
+    mm_panel<32>(S, o + 32, o, tid);
+    mm_syrk<32>(S, o + 32, o, tid);
+    diag32_factor_invert(S, ldiag, pv, o + 32, tid, status);
+    mm_inv_offdiag<32>(S, o + 32, o, tid);
+}
+}  // namespace
+
+#define DIAG_MARK(slot) do { if (dbg && tid == 0) dbg[slot] = clock64(); } while (0)
+__global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A, int64_t lda, int nb,
+                                                         double* __restrict__ Dinv, int64_t ldd, int* status,
+                                                         long long* dbg) {
+    extern __shared__ double dsm[];
+    double* S = dsm;
+    double* ldiag = dsm + DB * DLD;
+    double* pv = ldiag + DB;
+    const int tid = threadIdx.x;
+    DIAG_MARK(0);
+    // load the lower triangle (rows/cols >= nb padded with the identity)
+    for (int idx = tid; idx < DB * DB; idx += DTHREADS) {
+        const int r = idx % DB, c = idx / DB;
+        double v = 0.0;
+        if (r >= c) v = (r < nb) ? A[r + (int64_t)c * lda] : (r == c ? 1.0 : 0.0);
+        S[r * DLD + c] = v;
+    }
+    __syncthreads();
+    DIAG_MARK(1);
+    diag32_factor_invert(S, ldiag, pv, 0, tid, status);
+    DIAG_MARK(2);
+    mm_panel<32>(S, 32, 0, tid);
+    mm_syrk<32>(S, 32, 0, tid);
+    DIAG_MARK(3);
+    diag32_factor_invert(S, ldiag, pv, 32, tid, status);
+    mm_inv_offdiag<32>(S, 32, 0, tid);
+    DIAG_MARK(4);
+    mm_panel<64>(S, 64, 0, tid);
+    DIAG_MARK(5);
+    mm_syrk<64>(S, 64, 0, tid);
+    DIAG_MARK(6);
+    factor_invert_64(S, ldiag, pv, 64, tid, status);
+    DIAG_MARK(7);
+    mm_inv_offdiag<64>(S, 64, 0, tid);
+    DIAG_MARK(8);
+    for (int idx = tid; idx < DB * DB; idx += DTHREADS) {
+        const int r = idx % DB, c = idx / DB;
+        if (r < nb && c < nb) {
+            if (r > c) A[r + (int64_t)c * lda] = S[r * DLD + c];
+            else if (r == c) A[r + (int64_t)c * lda] = ldiag[r];
+            Dinv[r + (int64_t)c * ldd] = (r >= c) ? S[c * DLD + r] : 0.0;
+        }
+    }
+    __syncthreads();
+    DIAG_MARK(9);
+}
+
+// Right-looking Cholesky with one-panel look-ahead on two streams.
+//   main stream (critical path):  diag(k) -> panel(k) -> [wait bulk(k-1)] -> crit(k) -> diag(k+1) ...
+//   aux stream  (bulk work)     :  [wait panel(k)] -> bulk(k)
+// crit(k) is the rank-128 update of block column k+1 only, bulk(k) that of the remaining trailing matrix (columns
+// >= k+2); the serial diagonal-block kernels therefore overlap the large symmetric updates.
+int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv, int64_t ldd, int* d_status,
+                   CholLookahead* la) {
+    if (n <= 0) return GPIRT_B200_OK;
+    constexpr size_t smem = (size_t)(DB * DLD + 2 * DB) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        GP_CUDA(cudaFuncSetAttribute(k_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int nblk = (int)ceil_div(n, CHOL_NB);
+    const bool two = la && la->aux && nblk > 2;
+    if (two) {
+        while ((int)la->ev_panel.size() < nblk) {
+            cudaEvent_t e1, e2;
+            GP_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            GP_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            la->ev_panel.push_back(e1); la->ev_bulk.push_back(e2);
+        }
+    }
+    int last_bulk = -1;
+    for (int k = 0; k < nblk; ++k) {
+        const int k0 = k * CHOL_NB;
+        const int nb = min(CHOL_NB, n - k0);
+        double* Akk = A + (int64_t)k0 * (lda + 1);
+        static long long* dbg = nullptr;
+        static bool dbg_on = getenv("GPIRT_DIAG_DEBUG") != nullptr;
+        if (dbg_on && !dbg) cudaMalloc((void**)&dbg, 16 * sizeof(long long));
+        GP_LAUNCH(k_diag128, 1, DTHREADS, smem, stream, Akk, lda, nb, Dinv + k0, ldd, d_status, dbg_on ? dbg : nullptr);
+        GP_CUDA(cudaGetLastError());
+        if (dbg_on && k == 1) {
+            long long h[16];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "k_diag128 phases (cycles): load %lld | diag32 %lld | panel+syrk32 %lld | diag32+inv32 %lld | panel64 %lld | syrk64 %lld | f_i_64 %lld | inv64 %lld | store %lld | total %lld\n",
+                    h[1]-h[0], h[2]-h[1], h[3]-h[2], h[4]-h[3], h[5]-h[4], h[6]-h[5], h[7]-h[6], h[8]-h[7], h[9]-h[8], h[9]-h[0]);
+        }
+        const int rem = n - k0 - nb;
+        if (rem <= 0) break;
+        double* P = Akk + nb;  // rem x nb panel below the diagonal block
+        GemmArgs g;            // P <- P Dinv_k^T, in place: one 128-wide column tile, each CTA rewrites only rows it read
+        g.M = rem; g.N = nb; g.K = nb; g.A = P; g.lda = lda; g.B = Dinv + k0; g.ldb = ldd; g.C = P; g.ldc = lda;
+        g.force_big = 1;
+        GP_TRY(gemm_f64(stream, false, true, g));
+        double* A22 = Akk + (int64_t)nb * (lda + 1);
+        if (!two) {
+            GemmArgs u;        // A22 -= P P^T (lower triangle)
+            u.M = rem; u.N = rem; u.K = nb; u.A = P; u.lda = lda; u.B = P; u.ldb = lda;
+            u.C = A22; u.ldc = lda; u.alpha = -1.0; u.beta = 1.0; u.tri = TRI_C_LOWER;
+            GP_TRY(gemm_f64(stream, false, true, u));
+            continue;
+        }
+        const int nb1 = min(CHOL_NB, rem);   // width of block column k+1
+        GP_CUDA(cudaEventRecord(la->ev_panel[k], stream));
+        if (rem - nb1 > 0) {                 // bulk(k): columns >= k+2, on the aux stream
+            GP_CUDA(cudaStreamWaitEvent(la->aux, la->ev_panel[k], 0));
+            GemmArgs u;
+            u.M = rem - nb1; u.N = rem - nb1; u.K = nb; u.A = P + nb1; u.lda = lda; u.B = P + nb1; u.ldb = lda;
+            u.C = A22 + (int64_t)nb1 * (lda + 1); u.ldc = lda; u.alpha = -1.0; u.beta = 1.0; u.tri = TRI_C_LOWER;
+            GP_TRY(gemm_f64(la->aux, false, true, u));
+            GP_CUDA(cudaEventRecord(la->ev_bulk[k], la->aux));
+        }
+        if (last_bulk >= 0) GP_CUDA(cudaStreamWaitEvent(stream, la->ev_bulk[last_bulk], 0));   // bulk(k-1) also wrote column k+1
+        last_bulk = (rem - nb1 > 0) ? k : -1;
+        GemmArgs c;            // crit(k): block column k+1
+        c.M = rem; c.N = nb1; c.K = nb; c.A = P; c.lda = lda; c.B = P; c.ldb = lda;
+        c.C = A22; c.ldc = lda; c.alpha = -1.0; c.beta = 1.0; c.tri = TRI_C_LOWER;
+        GP_TRY(gemm_f64(stream, false, true, c));
+    }
+    if (two && last_bulk >= 0) GP_CUDA(cudaStreamWaitEvent(stream, la->ev_bulk[last_bulk], 0));
+    return GPIRT_B200_OK;
+}
+
+__global__ void k_scatter_block_inverses(const double* __restrict__ Dinv, int64_t ldd, int n, double* __restrict__ X,
+                                         int64_t ldx) {
+    // X(r, c) = Dinv(r, c mod 128) inside the 128 x 128 diagonal blocks; everything else was zeroed by the caller
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n || c >= n) return;
+    if (r / CHOL_NB == c / CHOL_NB) X[r + (int64_t)c * ldx] = Dinv[r + (int64_t)(c % CHOL_NB) * ldd];
+}
+
+int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv, int64_t ldd, double* X,
+                int64_t ldx, double* T, int64_t ldt) {
+    if (n <= 0) return GPIRT_B200_OK;
+    GP_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * n * sizeof(double), stream));
+    {
+        dim3 grid((unsigned)ceil_div(n, 128), (unsigned)n);
+        GP_LAUNCH(k_scatter_block_inverses, grid, 128, 0, stream, Dinv, ldd, n, X, ldx);
+        GP_CUDA(cudaGetLastError());
+    }
+    for (int64_t s = CHOL_NB; s < n; s *= 2) {
+        const int full_pairs = (int)(n / (2 * s));           // pairs whose second block is complete
+        const int64_t o_r = (int64_t)full_pairs * 2 * s;     // offset of a possible ragged pair
+        const int s2 = (int)std::min<int64_t>(s, n - (o_r + s));   // size of its second block (<= 0: none)
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool ragged = pass == 1;
+            if (!ragged && full_pairs == 0) continue;
+            if (ragged && s2 <= 0) continue;
+            const int64_t o = ragged ? o_r : 0;
+            const int rows = ragged ? s2 : (int)s;
+            GemmArgs a;   // T21 = L21 X11   (X11 lower triangular)
+            a.M = rows; a.N = (int)s; a.K = (int)s;
+            a.A = L + (o + s) + o * ldl; a.lda = ldl; a.B = X + o + o * ldx; a.ldb = ldx;
+            a.C = T + (o + s) + o * ldt; a.ldc = ldt; a.tri = TRI_B_LOWER;
+            a.batch = ragged ? 1 : full_pairs;
+            a.strideA = 2 * s * (ldl + 1); a.strideB = 2 * s * (ldx + 1); a.strideC = 2 * s * (ldt + 1);
+            GP_TRY(gemm_f64(stream, false, false, a));
+            GemmArgs b;   // X21 = -X22 T21  (X22 lower triangular)
+            b.M = rows; b.N = (int)s; b.K = rows;
+            b.A = X + (o + s) + (o + s) * ldx; b.lda = ldx; b.B = T + (o + s) + o * ldt; b.ldb = ldt;
+            b.C = X + (o + s) + o * ldx; b.ldc = ldx; b.alpha = -1.0; b.tri = TRI_A_LOWER;
+            b.batch = a.batch; b.strideA = 2 * s * (ldx + 1); b.strideB = 2 * s * (ldt + 1); b.strideC = 2 * s * (ldx + 1);
+            GP_TRY(gemm_f64(stream, false, false, b));
+        }
+    }
+    return GPIRT_B200_OK;
 }
 
 }  // namespace gpirt

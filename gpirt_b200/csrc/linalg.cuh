@@ -1,5 +1,7 @@
 // Blocked FP64 factorisation / triangular solves built on the DMMA GEMM (gemm_f64.cuh).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace gpirt {
@@ -22,5 +24,27 @@ int trsm_left_lower(cudaStream_t stream, bool trans, int n, int nrhs, const doub
 // X <- X L^-T  (solve X L^T = B in place; X is rows x n), used by the Cholesky panel step.
 int trsm_right_lower_t(cudaStream_t stream, int rows, int n, const double* L, int64_t ldl, const double* Dinv,
                        int64_t ldd, double* X, int64_t ldx);
+
+}  // namespace gpirt
+
+namespace gpirt {
+
+constexpr int CHOL_NB = 128;  // panel width of the right-looking factorisation; diagonal blocks done by one CTA
+
+// Right-looking blocked Cholesky (lower), panel width 128.  Per panel: k_diag128 factorises AND inverts the 128 x 128
+// diagonal block in one CTA; the panel below is multiplied by that inverse and the trailing matrix gets a rank-128
+// update, both on the DMMA GEMM.  Dinv128 (n x 128, ld ldd) receives the inverse of every diagonal block of L.
+struct CholLookahead {      // second stream + events for the one-panel look-ahead (owned by the caller)
+    cudaStream_t aux = nullptr;
+    std::vector<cudaEvent_t> ev_panel, ev_bulk;
+};
+int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv128, int64_t ldd, int* d_status,
+                   CholLookahead* la = nullptr);
+
+// X = L^-1 (n x n, lower; strict upper zero) by batched recursive doubling from the 128 x 128 block inverses:
+//   inv([[L11,0],[L21,L22]]) = [[X11,0],[-X22 L21 X11, X22]], all pairs of one level in a single batched GEMM launch.
+// T is n x n scratch.
+int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv128, int64_t ldd, double* X,
+                int64_t ldx, double* T, int64_t ldt);
 
 }  // namespace gpirt

@@ -31,6 +31,7 @@ struct gpirt_b200_sampler {
     uint32_t item_offset = 0;
     Comm comm;
     cudaStream_t stream = nullptr;
+    CholLookahead lookahead;
     bool has_missing = false;
     bool timing = true;
     uint32_t sweep_counter = 0;
@@ -40,7 +41,7 @@ struct gpirt_b200_sampler {
     double *yd = nullptr, *theta = nullptr, *theta_star = nullptr, *prior = nullptr, *beta = nullptr, *pm = nullptr,
            *psd = nullptr, *pstep = nullptr, *L = nullptr, *Dinv = nullptr, *f = nullptr, *Z = nullptr, *nu = nullptr,
            *fstar = nullptr, *Dmat = nullptr, *irf_sum = nullptr, *kstar = nullptr, *s = nullptr, *logPt = nullptr,
-           *partial = nullptr;
+           *partial = nullptr, *Linv = nullptr, *Tmp = nullptr, *kstar2 = nullptr;
     int *nprop = nullptr, *theta_idx = nullptr, *status = nullptr;  // status[0] chol, [1] ess, [2] theta-degenerate count
     unsigned long long* counters = nullptr;                        // [0] missing cells, [1] illegal cells
     static constexpr int N_CHUNKS = 32;
@@ -132,12 +133,14 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     }
     launches_at_create = g_launch_count;
     GP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    GP_CUDA(cudaStreamCreateWithFlags(&lookahead.aux, cudaStreamNonBlocking));
 
     const size_t nm = (size_t)ldn * m, Nm = (size_t)ldN * m;
     GP_TRY(alloc(y8, (size_t)ldy8 * m)); GP_TRY(alloc(yd, nm));
     GP_TRY(alloc(theta, (size_t)ldn)); GP_TRY(alloc(theta_star, (size_t)ldN)); GP_TRY(alloc(prior, (size_t)ldN));
     GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
-    GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * DIAG_NB));
+    GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * CHOL_NB));
+    GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * N_GRID));
     GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
     GP_TRY(alloc(kstar, (size_t)ldn * N_GRID)); GP_TRY(alloc(s, (size_t)ldN));
@@ -191,7 +194,10 @@ int gpirt_b200_sampler::step_rebuild() {
     GP_TRY(launch_se_cov(stream, theta, n, theta, n, 0.001, true, L, ldn));
     toc();
     tic(GPIRT_B200_T_CHOL);
-    GP_TRY(potrf_lower(stream, L, ldn, n, Dinv, ldn, status));
+    GP_TRY(potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, &lookahead));
+    toc();
+    tic(GPIRT_B200_T_TRTRI);   // L^-1 once per sweep: every triangular solve of draw_fstar becomes a triangular GEMM
+    GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
     toc();
     return GPIRT_B200_OK;
 }
@@ -228,24 +234,23 @@ int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
     GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));          // :17
     toc();
     tic(GPIRT_B200_T_TRSM);
-    GP_TRY(trsm_left_lower(stream, false, n, N, L, ldn, Dinv, ldn, kstar, ldn));             // :19 tmp = L^-1 K*
-    GP_TRY(launch_fstar_sd(stream, kstar, ldn, n, N, s));                                    // :20
+    // tmp = solve(trimatl(L), kstar) as the triangular product L^-1 K*                      :19
+    GP_TRY(gemm_f64(stream, false, false, G(n, N, n, Linv, ldn, kstar, ldn, kstar2, ldn, 1.0, 0.0, TRI_A_LOWER)));
+    GP_TRY(launch_fstar_sd(stream, kstar2, ldn, n, N, s));                                   // :20
     if (opts.fstar_mode == 0) {
-        // K*^T L^-T L^-1 f_j = (L^-T tmp)^T f_j : solve once for the 1001 grid columns instead of per item
-        GP_TRY(trsm_left_lower(stream, true, n, N, L, ldn, Dinv, ldn, kstar, ldn));
+        // K*^T L^-T L^-1 f_j = (L^-T tmp)^T f_j : one n x 1001 product instead of two solves per item
+        GP_TRY(gemm_f64(stream, true, false, G(n, N, n, Linv, ldn, kstar2, ldn, kstar, ldn, 1.0, 0.0, TRI_A_UPPER)));
         toc();
         tic(GPIRT_B200_T_FSTAR_GEMM);
         GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, f, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
         toc();
     } else {
         // literal: alpha_j = L^-T (L^-1 f_j) for every item (:3-8,:24), mean_j = K*^T alpha_j (:25)
-        GP_CUDA(cudaMemcpyAsync(Z, f, (size_t)ldn * m * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-        GP_TRY(trsm_left_lower(stream, false, n, m, L, ldn, Dinv, ldn, Z, ldn));
-        GP_TRY(trsm_left_lower(stream, true, n, m, L, ldn, Dinv, ldn, Z, ldn));
+        GP_TRY(gemm_f64(stream, false, false, G(n, m, n, Linv, ldn, f, ldn, Z, ldn, 1.0, 0.0, TRI_A_LOWER)));
+        GP_TRY(gemm_f64(stream, true, false, G(n, m, n, Linv, ldn, Z, ldn, nu, ldn, 1.0, 0.0, TRI_A_UPPER)));
         toc();
         tic(GPIRT_B200_T_FSTAR_GEMM);
-        GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));
-        GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, Z, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
+        GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, nu, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
         toc();
     }
     tic(GPIRT_B200_T_FSTAR_DRAW);
@@ -325,9 +330,13 @@ void gpirt_b200_sampler::destroy() {
     flush_timers();
     for (auto e : pool) cudaEventDestroy(e);
     pool.clear();
+    for (auto e : lookahead.ev_panel) cudaEventDestroy(e);
+    for (auto e : lookahead.ev_bulk) cudaEventDestroy(e);
+    lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
+    if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
     comm_destroy(comm);
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
-                    kstar, s, logPt, partial, nprop, theta_idx, status, counters};
+                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;

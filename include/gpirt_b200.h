@@ -116,7 +116,7 @@ enum gpirt_b200_timer {
     GPIRT_B200_T_FILL_Z = 0, GPIRT_B200_T_LZ_GEMM = 1, GPIRT_B200_T_ESS = 2, GPIRT_B200_T_KSTAR = 3,
     GPIRT_B200_T_TRSM = 4, GPIRT_B200_T_FSTAR_GEMM = 5, GPIRT_B200_T_FSTAR_DRAW = 6, GPIRT_B200_T_THETA_PREP = 7,
     GPIRT_B200_T_THETA_GEMM = 8, GPIRT_B200_T_ALLREDUCE = 9, GPIRT_B200_T_THETA_DRAW = 10, GPIRT_B200_T_BETA = 11,
-    GPIRT_B200_T_KBUILD = 12, GPIRT_B200_T_CHOL = 13, GPIRT_B200_TIMER_COUNT = 14
+    GPIRT_B200_T_KBUILD = 12, GPIRT_B200_T_CHOL = 13, GPIRT_B200_T_TRTRI = 14, GPIRT_B200_TIMER_COUNT = 15
 };
 int gpirt_b200_sampler_timings(gpirt_b200_sampler* s, double* ms, int64_t* calls, int reset);
 int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled); /* per-step events on (default) / off */

@@ -19,8 +19,8 @@ s.timings(reset=True)
 ms = s.sweep(sweeps)
 t = s.timings()
 n, m, N = cfg["n"], cfg["m"], 1001
-flops = {"lz_gemm": n * n * m, "fstar_gemm": 2.0 * n * N * m, "theta_gemm": 2.0 * n * N * m, "chol": n ** 3 / 3.0,
-         "trsm": 2.0 * n * n * N if mode == 0 else (n * n * N + 2.0 * n * n * m)}
+flops = {"lz_gemm": n * n * m, "fstar_gemm": 2.0 * n * N * m, "theta_gemm": 2.0 * n * N * m, "chol": n ** 3 / 3.0, "trtri": n ** 3 / 3.0,
+         "trsm": 2.0 * n * n * N if mode == 0 else (n * n * N + 2.0 * n * n * m)}  # triangular products: n^2 per RHS each
 print("workload %s n=%d m=%d: %.3f ms/sweep (%.1f sweeps/s), launches/sweep %.0f" % (wl, n, m, ms / sweeps, 1000 * sweeps / ms, s.launches() / (sweeps + 3)))
 tot = sum(v[0] for v in t.values())
 for k, (a, c) in t.items():
