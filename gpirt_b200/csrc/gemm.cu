@@ -4,9 +4,9 @@
 
 namespace gpirt {
 
-template <int BM, int BN, int WM, int WN, bool TA, bool TB>
+template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool BABS>
 static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
-    auto kern = gemm_f64_kernel<BM, BN, WM, WN, TA, TB>;
+    auto kern = gemm_f64_kernel<BM, BN, WM, WN, TA, TB, BABS>;
     static bool configured = false;  // per instantiation
     constexpr size_t smem = gemm_smem_bytes<BM, BN>();
     if (!configured) {
@@ -22,8 +22,17 @@ static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
 template <bool TA, bool TB>
 static int launch_layout(cudaStream_t stream, const GemmArgs& g) {
     const int64_t tiles128 = ceil_div(g.M, 128) * ceil_div(g.N, 128) * g.batch;
-    if (tiles128 >= 112 || g.force_big) return launch_cfg<128, 128, 4, 2, TA, TB>(stream, g);
-    return launch_cfg<64, 64, 2, 2, TA, TB>(stream, g);
+    if (g.b_abs) {  // only the observed-mask product of the theta step (op(B) = Y^T) takes |B|
+        if constexpr (!TA && TB) {
+            if (tiles128 >= 112 || g.force_big) return launch_cfg<128, 128, 4, 2, TA, TB, true>(stream, g);
+            return launch_cfg<64, 64, 2, 2, TA, TB, true>(stream, g);
+        } else {
+            set_last_error("gemm_f64: b_abs is only instantiated for op(A)=N, op(B)=T");
+            return GPIRT_B200_ERR_ARG;
+        }
+    }
+    if (tiles128 >= 112 || g.force_big) return launch_cfg<128, 128, 4, 2, TA, TB, false>(stream, g);
+    return launch_cfg<64, 64, 2, 2, TA, TB, false>(stream, g);
 }
 
 int gemm_f64(cudaStream_t stream, bool ta, bool tb, const GemmArgs& g) {

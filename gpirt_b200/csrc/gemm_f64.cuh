@@ -63,7 +63,7 @@ constexpr size_t gemm_smem_bytes() {
     return (size_t)GEMM_STAGES * (size_t)(BM + BN) * (GEMM_BK + GEMM_PAD) * sizeof(double);
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB>
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, bool BABS>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(const GemmArgs g) {
     constexpr int THREADS = WARPS_M * WARPS_N * 32;
     constexpr int BK = GEMM_BK, PAD = GEMM_PAD, STAGES = GEMM_STAGES;
@@ -98,31 +98,49 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
     const int gq = lane >> 2, tq = lane & 3;
     const int wm0 = (warp % WARPS_M) * WTM, wn0 = (warp / WARPS_M) * WTN;
 
-    auto load_tile = [&](int stage, int kt) {
+    // ---- loader state: every thread owns RA (RB) fixed (m,k) slots of the A (B) tile; only the k offset moves from
+    // one k-tile to the next, so the global pointers are advanced by a constant and the shared offsets are constants.
+    constexpr int RA = (BK * BM) / THREADS, RB = (BK * BN) / THREADS;
+    constexpr int A_SLOT = TA ? THREADS / BK : THREADS / BM;   // TA: rows of m per pass ; else rows of k per pass
+    constexpr int B_SLOT = TB ? THREADS / BN : THREADS / BK;   // TB: rows of k per pass ; else rows of n per pass
+    const int a_fast = TA ? tid % BK : tid % BM, a_slow = TA ? tid / BK : tid / BM;   // fast = contiguous index
+    const int b_fast = TB ? tid % BN : tid % BK, b_slow = TB ? tid / BN : tid / BK;
+    // TA: fast = k, slow = m.  !TA: fast = m, slow = k.   TB: fast = n, slow = k.  !TB: fast = k, slow = n.
+    const double* pa = TA ? gA + (int64_t)(k_begin + a_fast) + (int64_t)(m0 + a_slow) * g.lda
+                          : gA + (int64_t)(m0 + a_fast) + (int64_t)(k_begin + a_slow) * g.lda;
+    const double* pb = TB ? gB + (int64_t)(n0 + b_fast) + (int64_t)(k_begin + b_slow) * g.ldb
+                          : gB + (int64_t)(k_begin + b_fast) + (int64_t)(n0 + b_slow) * g.ldb;
+    const int64_t a_pass = (int64_t)A_SLOT * g.lda, b_pass = (int64_t)B_SLOT * g.ldb;      // pointer step between passes
+    const int64_t a_tile = TA ? (int64_t)BK : (int64_t)BK * g.lda;                         // pointer step between k-tiles
+    const int64_t b_tile = TB ? (int64_t)BK * g.ldb : (int64_t)BK;
+    const int a_soff = TA ? a_slow * LDA_S + a_fast : a_slow * LDA_S + a_fast;
+    const int b_soff = TB ? b_slow * LDB_S + b_fast : b_slow * LDB_S + b_fast;
+    // (TA: As[m][k] -> slow*LDA_S + fast ; !TA: As[k][m] -> slow*LDA_S + fast : same form, slow indexes the padded row)
+    const bool a_fix_ok = TA ? true : (m0 + a_fast < g.M);     // row validity that does not depend on the pass
+    const bool b_fix_ok = TB ? (n0 + b_fast < g.N) : true;
+
+    // issue passes [r0, r1) of the A and B loads of k-tile kt into `stage`
+    auto load_part = [&](int stage, int kt, int part, int nparts) {
         const int k0 = k_begin + kt * BK;
-        double* as = As + stage * A_STAGE;
-        double* bs = Bs + stage * B_STAGE;
+        double* as = As + stage * A_STAGE + a_soff;
+        double* bs = Bs + stage * B_STAGE + b_soff;
+        const double* ga = pa + (int64_t)kt * a_tile;
+        const double* gb = pb + (int64_t)kt * b_tile;
 #pragma unroll
-        for (int r = 0; r < (BK * BM) / THREADS; ++r) {
-            const int e = tid + r * THREADS;
-            int m, k;
-            if (TA) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
-            const bool ok = (m0 + m < g.M) && (k0 + k < k_end);
-            const double* src = ok ? (TA ? gA + (int64_t)(k0 + k) + (int64_t)(m0 + m) * g.lda
-                                         : gA + (int64_t)(m0 + m) + (int64_t)(k0 + k) * g.lda)
-                                   : gA;
-            cp_async_f64(TA ? as + m * LDA_S + k : as + k * LDA_S + m, src, ok);
+        for (int r = 0; r < RA; ++r) {
+            if (r * nparts / RA != part) continue;
+            bool ok;
+            if (TA) ok = (k0 + a_fast < k_end) && (m0 + a_slow + r * A_SLOT < g.M);
+            else ok = a_fix_ok && (k0 + a_slow + r * A_SLOT < k_end);
+            cp_async_f64(as + r * A_SLOT * LDA_S, ok ? ga + r * a_pass : gA, ok);
         }
 #pragma unroll
-        for (int r = 0; r < (BK * BN) / THREADS; ++r) {
-            const int e = tid + r * THREADS;
-            int n, k;
-            if (TB) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
-            const bool ok = (n0 + n < g.N) && (k0 + k < k_end);
-            const double* src = ok ? (TB ? gB + (int64_t)(n0 + n) + (int64_t)(k0 + k) * g.ldb
-                                         : gB + (int64_t)(k0 + k) + (int64_t)(n0 + n) * g.ldb)
-                                   : gB;
-            cp_async_f64(TB ? bs + k * LDB_S + n : bs + n * LDB_S + k, src, ok);
+        for (int r = 0; r < RB; ++r) {
+            if (r * nparts / RB != part) continue;
+            bool ok;
+            if (TB) ok = b_fix_ok && (k0 + b_slow + r * B_SLOT < k_end);
+            else ok = (k0 + b_fast < k_end) && (n0 + b_slow + r * B_SLOT < g.N);
+            cp_async_f64(bs + r * B_SLOT * LDB_S, ok ? gb + r * b_pass : gB, ok);
         }
     };
 
@@ -134,37 +152,40 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nkt) load_tile(s, s);
+        if (s < nkt) load_part(s, s, 0, 1);
         cp_async_commit();
     }
+    constexpr int KSTEPS = BK / 4;
     for (int it = 0; it < nkt; ++it) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         const int nxt = it + STAGES - 1;
-        if (nxt < nkt) load_tile(nxt % STAGES, nxt);
-        cp_async_commit();
+        const bool do_load = nxt < nkt;
+        const int lstage = nxt % STAGES;
         const double* as = As + (it % STAGES) * A_STAGE;
         const double* bs = Bs + (it % STAGES) * B_STAGE;
 #pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            const int kk = ks * 4;
+            if (do_load) load_part(lstage, nxt, ks, KSTEPS);   // the next tile's loads are spread over the k-steps
             double a[MI], b[NI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
                 const int m = wm0 + i * 8 + gq, k = kk + tq;
-                double v = TA ? as[m * LDA_S + k] : as[k * LDA_S + m];
-                a[i] = v;
+                a[i] = TA ? as[m * LDA_S + k] : as[k * LDA_S + m];
             }
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
                 const int n = wn0 + j * 8 + gq, k = kk + tq;
                 double w = TB ? bs[k * LDB_S + n] : bs[n * LDB_S + k];
-                b[j] = g.b_abs ? fabs(w) : w;
+                b[j] = BABS ? fabs(w) : w;
             }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
