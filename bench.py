@@ -94,7 +94,7 @@ def cpu_reference_sweeps(cfg, data, steps, warmup, budget_s, threads):
     n, m = cfg["n"], cfg["m"]
     use_ref = os.path.exists(O.REF_SO)
     O.set_blas_threads(threads)
-    per_item = 2.2e-8 * n * N_GRID + 1.2e-8 * n * n       # rough seconds/item (theta grid loop + three O(n^2) passes)
+    per_item = 1.35e-7 * n * N_GRID + 1.2e-8 * n * n       # rough seconds/item (theta grid loop + three O(n^2) passes)
     fixed = 6e-11 * n ** 3 / max(1, min(threads, 8)) + 2e-8 * n * n
     m_s = int(max(4, min(m, 128, (budget_s / max(1, steps + warmup) - fixed) / per_item)))
     y = np.asfortranarray(data["y"][:, :m_s])
@@ -207,11 +207,15 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid_t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid_t = torch.tensor(list(G.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid_t, 0)
-        uid = bytes(uid_t.cpu().tolist())
+
+        def fresh_uid():
+            # one ncclUniqueId per communicator: rank 0 creates it, torch.distributed carries it to the other ranks
+            uid_t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid_t = torch.tensor(list(G.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid_t, 0)
+            return bytes(uid_t.cpu().tolist())
+        uid = fresh_uid()
     data = synthetic.make(n, m)
     # contiguous item block of this rank
     per = (m + world - 1) // world
@@ -281,17 +285,18 @@ def main():
     # ------------------------------------------------------------------ end-to-end through the public call (host buffers)
     if not args.no_e2e:
         from gpirt_b200 import ResponseMatrix
-        Ke = min(K, 8)   # f draws are n*m*8 bytes per stored sweep on the host; bound the host allocation
+        Ke = min(K, 12)   # f draws are n*m*8 bytes per stored sweep on the host; bound the host allocation
         yrm = ResponseMatrix(y_loc)
-        shard = (rank, world, m, j0, uid) if world > 1 else None
         common = dict(beta_prior_means=data["pm"][:, j0:j1], beta_prior_sds=data["psd"][:, j0:j1],
                       beta_proposal_sds=data["pstep"][:, j0:j1], theta_init=data["theta_init"], seed=synthetic.SEED,
-                      device=local_rank, shard=shard, fstar_mode=args.fstar_mode)
-        G.gpirtMCMC(yrm, 1, 0, **common)     # warm the call path (allocator, pinning)
+                      device=local_rank, fstar_mode=args.fstar_mode)
+        shard = (rank, world, m, j0, fresh_uid()) if world > 1 else None
+        G.gpirtMCMC(yrm, 1, 0, shard=shard, **common)     # warm the call path (allocator, pinning)
+        shard = (rank, world, m, j0, fresh_uid()) if world > 1 else None
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        out = G.gpirtMCMC(yrm, Ke, 0, **common)
+        out = G.gpirtMCMC(yrm, Ke, 0, shard=shard, **common)
         el = time.perf_counter() - t0
         if dist is not None:
             import torch

@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, src.replace(".cu", ".o")) for src in SOURCES]
     if jobs or force or not os.path.exists(LIB):
-        run([NVCC, "-shared", "--cudart", "static", "-o", LIB] + objs + ["-ldl"])
+        run([NVCC, "-shared", "--cudart", "static", "-o", LIB] + objs + ["-ldl", "-lpthread"])
     return LIB
 
 

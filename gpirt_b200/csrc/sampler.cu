@@ -2,7 +2,11 @@
 // (src/gpirtMCMC.cpp:68-78 / :87-97) as a fixed sequence of kernel launches on one stream, and gpirt_b200_mcmc(),
 // the drop-in for gpirtMCMC() (src/gpirtMCMC.cpp:5-117).
 #include <cstdarg>
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <ctime>
+#include <thread>
 #include <vector>
 
 #include "comm.cuh"
@@ -342,6 +346,79 @@ void gpirt_b200_sampler::destroy() {
     stream = nullptr;
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Host side of draw storage: the caller's f array is ordinary pageable (R-allocated) memory, never touched before.
+// A slice goes device -> pinned bounce buffer in chunks over PCIe by DMA, and a few host threads copy each chunk into
+// the caller's array as soon as its DMA has landed (first-touch page faults are spread over the threads).
+// ----------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Bounce {
+    double* buf[2] = {nullptr, nullptr};
+    size_t cap = 0;
+    std::vector<cudaEvent_t> ev;
+    ~Bounce() { for (auto p : buf) if (p) cudaFreeHost(p); }
+    int ensure(size_t count) {
+        if (count <= cap) return GPIRT_B200_OK;
+        for (auto& p : buf) { if (p) cudaFreeHost(p); p = nullptr; }
+        cap = 0;
+        for (auto& p : buf)
+            if (cudaHostAlloc((void**)&p, count * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return GPIRT_B200_ERR_NOMEM;
+            }
+        cap = count;
+        return GPIRT_B200_OK;
+    }
+};
+Bounce g_bounce;   // process-wide, reused across calls
+
+int host_threads_for_copy() {
+    const char* e = getenv("GPIRT_COPY_THREADS");
+    int t = e ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    return t < 1 ? 1 : (t > 32 ? 32 : t);
+}
+
+// dst (pageable host) <- src (device), count doubles, via bounce buffer `b` on `stream`
+int chunked_d2h(double* dst, const double* src, size_t count, int b, cudaStream_t stream) {
+    const size_t chunk = (size_t)4 << 20;   // 4 Mi doubles = 32 MiB
+    const int nchunks = (int)((count + chunk - 1) / chunk);
+    if (g_bounce.ensure(count) != GPIRT_B200_OK) {   // no pinned memory: plain (driver-staged) copy
+        GP_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA(cudaStreamSynchronize(stream));
+        return GPIRT_B200_OK;
+    }
+    while ((int)g_bounce.ev.size() < nchunks) {
+        cudaEvent_t e;
+        GP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g_bounce.ev.push_back(e);
+    }
+    double* bb = g_bounce.buf[b];
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t off = (size_t)c * chunk, len = std::min(chunk, count - off);
+        GP_CUDA(cudaMemcpyAsync(bb + off, src + off, len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA(cudaEventRecord(g_bounce.ev[c], stream));
+    }
+    const int T = std::min(host_threads_for_copy(), nchunks);
+    std::atomic<int> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            if (cudaEventSynchronize(g_bounce.ev[c]) != cudaSuccess) { failed = 1; break; }
+            const size_t off = (size_t)c * chunk, len = std::min(chunk, count - off);
+            std::memcpy(dst + off, bb + off, len * sizeof(double));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (failed) { set_last_error("device-to-host copy of a draw slice failed"); return GPIRT_B200_ERR_CUDA; }
+    return GPIRT_B200_OK;
+}
+}  // namespace
+
 // ======================================================================================================================
 // C ABI
 // ======================================================================================================================
@@ -506,28 +583,62 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     }
     const bool keep_f = !(opts && opts->skip_f_draws);
     if (keep_f && !f_out) { set_last_error("f_out is NULL but f draws were requested"); return GPIRT_B200_ERR_ARG; }
+    const bool trace = getenv("GPIRT_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    double t_a = now();
     gpirt_b200_sampler* s = nullptr;
     GP_TRY(gpirt_b200_sampler_create(&s, y, n, m, theta_init, pm, psd, pstep, opts));
     s->timing = false;
-    struct Guard { gpirt_b200_sampler* s; double* pinned; ~Guard() { if (pinned) cudaHostUnregister(pinned); gpirt_b200_sampler_destroy(s); } } guard{s, nullptr};
+    double t_b = now();
+    // Draw storage overlaps the next sweep: after sweep t the state is snapshotted device-to-device (cheap), the host
+    // enqueues sweep t+1, and only then blocks in the device-to-host copy of snapshot t on a second stream.
+    struct Guard {
+        gpirt_b200_sampler* s; cudaStream_t copy; cudaEvent_t ev[2]; double* snap_f[2]; double* snap_small[2];
+        ~Guard() {
+            if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
+            for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); if (snap_f[i]) cudaFree(snap_f[i]); if (snap_small[i]) cudaFree(snap_small[i]); }
+            gpirt_b200_sampler_destroy(s);
+        }
+    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     const int S1 = sample_iterations + 1;
     const size_t nm = (size_t)n * m;
-    std::vector<double> th((size_t)n);
-    // pin the caller's f array so the per-iteration slices go out by DMA at full PCIe rate (best effort)
-    if (keep_f && cudaHostRegister(f_out, nm * S1 * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) guard.pinned = f_out;
-    else cudaGetLastError();
-
+    std::vector<double> small((size_t)n + 2 * (size_t)m);
+    GP_CUDA(cudaStreamCreateWithFlags(&gd.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        GP_CUDA(cudaEventCreateWithFlags(&gd.ev[i], cudaEventDisableTiming));
+        GP_CUDA(cudaMalloc((void**)&gd.snap_small[i], small.size() * sizeof(double)));
+        if (keep_f) GP_CUDA(cudaMalloc((void**)&gd.snap_f[i], nm * sizeof(double)));
+    }
+    double t_c = now();
     int rc = s->init_draws();
     if (rc) return rc;
-    auto store = [&](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
-        GP_CUDA(cudaMemcpyAsync(th.data(), s->theta, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        GP_CUDA(cudaMemcpyAsync(beta_out + (size_t)slot * 2 * m, s->beta, 2 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        if (keep_f) GP_TRY(download_padded(f_out + (size_t)slot * nm, s->f, s->ldn, (int)n, (int)m, s->stream));
-        GP_CUDA(cudaStreamSynchronize(s->stream));
-        for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * S1 + slot] = th[i];
+    double t_d = now(), t_store = 0.0;
+    // snapshot(slot): main stream copies theta | beta (and f, tightly packed) into buffer slot & 1 and records the event
+    auto snapshot = [&](int slot) -> int {
+        const int b = slot & 1;
+        GP_CUDA(cudaMemcpyAsync(gd.snap_small[b], s->theta, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        GP_CUDA(cudaMemcpyAsync(gd.snap_small[b] + n, s->beta, 2 * (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        if (keep_f)
+            GP_CUDA(cudaMemcpy2DAsync(gd.snap_f[b], (size_t)n * sizeof(double), s->f, s->ldn * sizeof(double), (size_t)n * sizeof(double),
+                                      (size_t)m, cudaMemcpyDeviceToDevice, s->stream));
+        GP_CUDA(cudaEventRecord(gd.ev[b], s->stream));
         return GPIRT_B200_OK;
     };
-    GP_TRY(store(0));                                                               // :53-55
+    // drain(slot): copy stream waits for the snapshot, then the host blocks in the device-to-host copies
+    auto drain = [&](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
+        const double ts0 = now();
+        const int b = slot & 1;
+        GP_CUDA(cudaStreamWaitEvent(gd.copy, gd.ev[b], 0));
+        GP_CUDA(cudaMemcpyAsync(small.data(), gd.snap_small[b], small.size() * sizeof(double), cudaMemcpyDeviceToHost, gd.copy));
+        if (keep_f) GP_TRY(chunked_d2h(f_out + (size_t)slot * nm, gd.snap_f[b], nm, b, gd.copy));
+        GP_CUDA(cudaStreamSynchronize(gd.copy));
+        for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * S1 + slot] = small[i];
+        std::memcpy(beta_out + (size_t)slot * 2 * m, small.data() + n, 2 * (size_t)m * sizeof(double));
+        t_store += now() - ts0;
+        return GPIRT_B200_OK;
+    };
+    GP_TRY(snapshot(0));                                                            // :53-55 initial values
+    int pending = 0;                                                                // slot whose snapshot is not drained yet
     const int total = sample_iterations + burn_iterations;
     const double inc = total > 0 ? 100.0 / total : 0.0;
     double progress = 0.0;
@@ -535,9 +646,16 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
         if (cb && cb(progress, cb_ctx)) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
         progress += inc;
         const bool sampling = iter >= burn_iterations;
-        GP_TRY(s->sweep(sampling ? 1 : 0));
-        if (sampling) GP_TRY(store(iter - burn_iterations + 1));                    // :99-103
+        GP_TRY(s->sweep(sampling ? 1 : 0));                                         // enqueue sweep (asynchronous)
+        if (pending >= 0) { GP_TRY(drain(pending)); pending = -1; }                 // previous slot goes out while it runs
+        else if ((iter & 7) == 7) GP_CUDA(cudaStreamSynchronize(s->stream));         // keep progress / interrupts honest in burn-in
+        if (sampling) {
+            const int slot = iter - burn_iterations + 1;                            // :99-103
+            GP_TRY(snapshot(slot));
+            pending = slot;
+        }
     }
+    if (pending >= 0) GP_TRY(drain(pending));
     GP_CUDA(cudaStreamSynchronize(s->stream));
     GP_TRY(s->check_status());
     // IRFs = plogis(IRFs / S)   (:106-111; S = 0 gives NaN exactly as the reference's 0 * inf)
@@ -546,6 +664,9 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     GP_CUDA(cudaMemcpyAsync(irf_out, s->Dmat, (size_t)N_GRID * m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     GP_CUDA(cudaStreamSynchronize(s->stream));
     if (cb) cb(100.0, cb_ctx);
+    if (trace)
+        fprintf(stderr, "gpirt_b200_mcmc: create %.3fs, copy buffers %.3fs, init draws %.3fs, %d sweeps + stores %.3fs (stores %.3fs)\n",
+                t_b - t_a, t_c - t_b, t_d - t_c, total, now() - t_d, t_store);
     return GPIRT_B200_OK;
 }
 

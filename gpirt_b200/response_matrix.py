@@ -27,6 +27,7 @@ class ResponseMatrix(np.ndarray):
         obj = np.asfortranarray(np.asarray(arr, dtype=np.float64)).view(cls)
         obj.rownames = rownames
         obj.colnames = colnames
+        obj._values_ok = None
         return obj
 
     def __array_finalize__(self, obj):
@@ -34,6 +35,7 @@ class ResponseMatrix(np.ndarray):
             return
         self.rownames = getattr(obj, "rownames", None)
         self.colnames = getattr(obj, "colnames", None)
+        self._values_ok = None   # cache of the {NA,-1,1} scan; views and slices start unchecked
 
 
 def _is_na(v):
@@ -144,7 +146,9 @@ def response_matrix(data, response_codes=None):
         warnings.warn("Item" + ("s " if nu > 1 else " ") + _printc(which) + (" were" if nu > 1 else " was") +
                       " discarded as unanimous.", ResponseMessage, stacklevel=2)
     kept_names = None if cnames is None else [c for c, u in zip(cnames, unanimous) if not u]
-    return ResponseMatrix(kept, rownames=rnames, colnames=kept_names)
+    out = ResponseMatrix(kept, rownames=rnames, colnames=kept_names)
+    out._values_ok = True
+    return out
 
 
 def is_response_matrix(x):
@@ -153,8 +157,17 @@ def is_response_matrix(x):
         return False
     if x.ndim != 2:
         return False
-    a = np.asarray(x)
-    return bool(np.all(np.isnan(a) | (a == 1.0) | (a == -1.0)))
+    if x._values_ok is None:   # one O(nm) scan per object (arrays are not expected to be mutated afterwards)
+        a = np.asarray(x)
+        ok = True
+        step = max(1, (1 << 22) // max(1, a.shape[0]))
+        for j0 in range(0, a.shape[1], step):
+            blk = a[:, j0:j0 + step]
+            if not np.all(np.isnan(blk) | (np.abs(blk) == 1.0)):
+                ok = False
+                break
+        x._values_ok = ok
+    return bool(x._values_ok)
 
 
 def as_response_matrix(x, response_codes=None):
