@@ -207,19 +207,15 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from gpirt_b200.sharding import share_unique_id
 
-        def fresh_uid():
-            # one ncclUniqueId per communicator: rank 0 creates it, torch.distributed carries it to the other ranks
-            uid_t = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                uid_t = torch.tensor(list(G.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-            dist.broadcast(uid_t, 0)
-            return bytes(uid_t.cpu().tolist())
+        def fresh_uid():   # one ncclUniqueId per communicator
+            return share_unique_id(dist, rank, G.nccl_unique_id, device="cuda")
         uid = fresh_uid()
     data = synthetic.make(n, m)
     # contiguous item block of this rank
-    per = (m + world - 1) // world
-    j0, j1 = min(m, rank * per), min(m, (rank + 1) * per)
+    from gpirt_b200.sharding import item_block
+    j0, j1 = item_block(m, rank, world)
     y_loc = np.asfortranarray(data["y"][:, j0:j1])
     kw = dict(seed=synthetic.SEED, device=local_rank, fstar_mode=args.fstar_mode)
     if world > 1:
