@@ -13,7 +13,7 @@ static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
         GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)g.batch);
+    dim3 grid((unsigned)(ceil_div(g.N, BN) * ceil_div(g.M, BM)), 1, (unsigned)g.batch);
     GP_LAUNCH(kern, grid, dim3(WM * WN * 32), smem, stream, g);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;

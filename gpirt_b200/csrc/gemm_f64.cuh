@@ -43,6 +43,7 @@ struct GemmArgs {
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_PAD = 4;
+constexpr int GEMM_GROUP_N = 8;
 
 __device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* gmem_src, bool pred) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -79,10 +80,21 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
 
-    // grid: x = column tiles (fastest: neighbouring CTAs share the A row panel in L2), y = row tiles, z = batch
-    const int mtiles = (g.M + BM - 1) / BM;
-    const int mt = (g.tri == TRI_A_LOWER) ? (mtiles - 1 - (int)blockIdx.y) : (int)blockIdx.y;  // heaviest rows first
-    const int m0 = mt * BM, n0 = (int)blockIdx.x * BN;
+    // Tile order (1-D grid per batch entry): column tiles are taken in groups of GEMM_GROUP_N; inside a group the CTAs
+    // walk the row tiles (heaviest first when op(A) is lower triangular) with the group's column tiles innermost.  A
+    // group's B panel (GROUP_N x 128 columns) then stays in L2 while every row tile consumes it, instead of the whole
+    // B matrix being streamed from HBM once per row tile.
+    const int mtiles = (g.M + BM - 1) / BM, ntiles = (g.N + BN - 1) / BN;
+    int mt, nt;
+    {
+        const int lin = (int)blockIdx.x, per_group = GEMM_GROUP_N * mtiles;
+        const int grp = lin / per_group, rem = lin % per_group;
+        const int gw = min(GEMM_GROUP_N, ntiles - grp * GEMM_GROUP_N);   // width of this (possibly last, narrower) group
+        mt = rem / gw;
+        nt = grp * GEMM_GROUP_N + rem % gw;
+        if (g.tri == TRI_A_LOWER) mt = mtiles - 1 - mt;
+    }
+    const int m0 = mt * BM, n0 = nt * BN;
     if (g.tri == TRI_C_LOWER && n0 > m0 + BM - 1) return;  // tile entirely above the diagonal
     const double* __restrict__ gA = g.A + (int64_t)blockIdx.z * g.strideA;
     const double* __restrict__ gB = g.B + (int64_t)blockIdx.z * g.strideB;
