@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the Gibbs sweep: covariance builder, response ingest, Philox fills, the batched elliptical
 // slice sampler with the fused logistic log-likelihood, f* finishing draw, theta grid sampler, beta Metropolis step.
 #include "kernels.cuh"
+#include "softplus_table.cuh"
 
 namespace gpirt {
 
@@ -142,7 +143,8 @@ constexpr int ESS_ITER_CAP = 10000;
 template <int EPT>
 __global__ void __launch_bounds__(512) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
                       int64_t ldy, const double* __restrict__ theta, const double* __restrict__ beta, int n, RngKey key,
-                      uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status) {
+                      uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status,
+                      const double* __restrict__ sp) {
     __shared__ double red[2][32];
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const uint32_t item = item_offset + (uint32_t)j;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(512) k_ess(double* __restrict__ f, const doubl
     double part = 0.0;
 #pragma unroll
     for (int e = 0; e < EPT; ++e)
-        if (yv[e] != 0.0) part -= ll_term(yv[e] * (fv[e] + gm[e]));
+        if (yv[e] != 0.0) part -= ll_term_fast(sp, yv[e] * (fv[e] + gm[e]));
     const double ll_cur = block_sum(part, red[0]);
     const double u = rng_uniform(key, P_ESS_U, item, 0u);
     const double log_y = ll_cur + log(u);                                            // draw-f.cpp:28-29
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(512) k_ess(double* __restrict__ f, const doubl
         for (int e = 0; e < EPT; ++e)
             if (yv[e] != 0.0) {
                 const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
-                part -= ll_term(yv[e] * (fp + gm[e]));
+                part -= ll_term_fast(sp, yv[e] * (fp + gm[e]));
             }
         const double ll_new = block_sum(part, red[iter & 1]);
         if (ll_new > log_y) break;                                                   // :45 strict
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, con
                                                      const int8_t* __restrict__ y8, int64_t ldy,
                                                      const double* __restrict__ theta, const double* __restrict__ beta,
                                                      int n, RngKey key, uint32_t item_offset, int* __restrict__ nprop,
-                                                     int* __restrict__ status) {
+                                                     int* __restrict__ status, const double* __restrict__ sp) {
     __shared__ double red[2][32];
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const uint32_t item = item_offset + (uint32_t)j;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, con
     double part = 0.0;
     for (int i = tid; i < n; i += T) {
         const double yv = (double)yj[i];
-        if (yv != 0.0) part -= ll_term(yv * (fj[i] + fma(theta[i], b1, b0)));
+        if (yv != 0.0) part -= ll_term_fast(sp, yv * (fj[i] + fma(theta[i], b1, b0)));
     }
     const double ll_cur = block_sum(part, red[0]);
     const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, con
             const double yv = (double)yj[i];
             if (yv != 0.0) {
                 const double fp = __dadd_rn(__dmul_rn(fj[i], c), __dmul_rn(nj[i], s));
-                part -= ll_term(yv * (fp + fma(theta[i], b1, b0)));
+                part -= ll_term_fast(sp, yv * (fp + fma(theta[i], b1, b0)));
             }
         }
         const double ll_new = block_sum(part, red[iter & 1]);
@@ -256,12 +258,14 @@ int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const i
     if (m <= 0) return GPIRT_B200_OK;
     int ept, threads;
     item_cta_shape(n, ept, threads);
+    const double* sp = nullptr;
+    GP_TRY(softplus_table(&sp));
     switch (ept) {
-        case 1: GP_LAUNCH(k_ess<1>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
-        case 2: GP_LAUNCH(k_ess<2>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
-        case 4: GP_LAUNCH(k_ess<4>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
-        case 8: GP_LAUNCH(k_ess<8>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
-        default: GP_LAUNCH(k_ess_stream, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status); break;
+        case 1: GP_LAUNCH(k_ess<1>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        case 2: GP_LAUNCH(k_ess<2>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        case 4: GP_LAUNCH(k_ess<4>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        case 8: GP_LAUNCH(k_ess<8>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        default: GP_LAUNCH(k_ess_stream, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
     }
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -465,7 +469,7 @@ template <int EPT>
 __global__ void __launch_bounds__(512) k_beta(double* __restrict__ beta, const double* __restrict__ f, int64_t ld, const int8_t* __restrict__ y8,
                        int64_t ldy, const double* __restrict__ theta, const double* __restrict__ pm,
                        const double* __restrict__ psd, const double* __restrict__ pstep, int n, RngKey key,
-                       uint32_t item_offset) {
+                       uint32_t item_offset, const double* __restrict__ sp) {
     __shared__ double red[4][32];
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const uint32_t item = item_offset + (uint32_t)j;
@@ -478,6 +482,7 @@ __global__ void __launch_bounds__(512) k_beta(double* __restrict__ beta, const d
     }
     double cv[2] = {beta[2 * j], beta[2 * j + 1]};
     double pv[2] = {cv[0], cv[1]};
+    double cv_ll = 0.0;   // ll_bar(rho, y, X * cv): the reference recomputes it for k = 1 (:28); it is the value kept from k = 0
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
@@ -488,14 +493,14 @@ __global__ void __launch_bounds__(512) k_beta(double* __restrict__ beta, const d
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
             if (yv[e] != 0.0) {
-                part_p -= ll_term(yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27  ll_bar(rho, y, X * pv)
-                part_c -= ll_term(yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));      // :28  ll_bar(rho, y, X * cv)
+                part_p -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27  ll_bar(rho, y, X * pv)
+                if (k == 0) part_c -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
             }
         const double pv_ll = block_sum(part_p, red[2 * k]);
-        const double cv_ll = block_sum(part_c, red[2 * k + 1]);
+        if (k == 0) cv_ll = block_sum(part_c, red[2 * k + 1]);
         const double r = pv_prior + pv_ll - cv_prior - cv_ll;                       // :29
         const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
-        if (log(u) < r) cv[k] = pv[k]; else pv[k] = cv[k];                          // :30-35
+        if (log(u) < r) { cv[k] = pv[k]; cv_ll = pv_ll; } else pv[k] = cv[k];       // :30-35
     }
     if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
 }
@@ -504,7 +509,8 @@ __global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta,
                                                       const int8_t* __restrict__ y8, int64_t ldy,
                                                       const double* __restrict__ theta, const double* __restrict__ pm,
                                                       const double* __restrict__ psd, const double* __restrict__ pstep,
-                                                      int n, RngKey key, uint32_t item_offset) {
+                                                      int n, RngKey key, uint32_t item_offset,
+                                                      const double* __restrict__ sp) {
     __shared__ double red[4][32];
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const uint32_t item = item_offset + (uint32_t)j;
@@ -523,8 +529,8 @@ __global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta,
             const double yv = (double)yj[i];
             if (yv != 0.0) {
                 const double fi = fj[i], ti = theta[i];
-                part_p -= ll_term(yv * (fi + fma(ti, pv[1], pv[0])));
-                part_c -= ll_term(yv * (fi + fma(ti, cv[1], cv[0])));
+                part_p -= ll_term_fast(sp, yv * (fi + fma(ti, pv[1], pv[0])));
+                part_c -= ll_term_fast(sp, yv * (fi + fma(ti, cv[1], cv[0])));
             }
         }
         const double pv_ll = block_sum(part_p, red[2 * k]);
@@ -543,12 +549,14 @@ int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, cons
     if (m <= 0) return GPIRT_B200_OK;
     int ept, threads;
     item_cta_shape(n, ept, threads);
+    const double* sp = nullptr;
+    GP_TRY(softplus_table(&sp));
     switch (ept) {
-        case 1: GP_LAUNCH(k_beta<1>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
-        case 2: GP_LAUNCH(k_beta<2>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
-        case 4: GP_LAUNCH(k_beta<4>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
-        case 8: GP_LAUNCH(k_beta<8>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
-        default: GP_LAUNCH(k_beta_stream, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset); break;
+        case 1: GP_LAUNCH(k_beta<1>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        case 2: GP_LAUNCH(k_beta<2>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        case 4: GP_LAUNCH(k_beta<4>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        case 8: GP_LAUNCH(k_beta<8>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        default: GP_LAUNCH(k_beta_stream, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
     }
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -556,7 +564,8 @@ int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, cons
 
 // ll_bar per column with explicit mu and double y (host-API helper mirroring log-likelihood.cpp:25-37)
 __global__ void __launch_bounds__(256) k_ll_bar(const double* __restrict__ f, const double* __restrict__ y,
-                                                const double* __restrict__ mu, int n, double* __restrict__ out) {
+                                                const double* __restrict__ mu, int n, double* __restrict__ out,
+                                                const double* __restrict__ sp) {
     __shared__ double red[32];
     const int j = blockIdx.x;
     double part = 0.0;
@@ -564,14 +573,16 @@ __global__ void __launch_bounds__(256) k_ll_bar(const double* __restrict__ f, co
         const double yi = y[i + (int64_t)j * n];
         if (isnan(yi)) continue;
         const double g = f[i + (int64_t)j * n] + mu[i + (int64_t)j * n];
-        part -= ll_term(yi * g);
+        part -= ll_term_fast(sp, yi * g);
     }
     const double tot = block_sum(part, red);
     if (threadIdx.x == 0) out[j] = tot;
 }
 int launch_ll_bar(cudaStream_t st, const double* f, const double* y, const double* mu, int n, int m, double* out) {
     if (m <= 0) return GPIRT_B200_OK;
-    GP_LAUNCH(k_ll_bar, (unsigned)m, 256, 0, st, f, y, mu, n, out);
+    const double* sp = nullptr;
+    GP_TRY(softplus_table(&sp));
+    GP_LAUNCH(k_ll_bar, (unsigned)m, 256, 0, st, f, y, mu, n, out, sp);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
 }

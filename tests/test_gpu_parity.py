@@ -115,6 +115,21 @@ def test_trsm_lower(G, O, n, r, trans):
     assert np.max(np.abs(resid)) <= 1e-11 * max(1.0, np.abs(got).max())
 
 
+def test_ll_bar_extremes(G, O):
+    """the table-driven log(1+exp(-a)) against the literal formula over the whole range, incl. the overflow quirk"""
+    a = np.concatenate([np.linspace(-60, 60, 4001), [-745.0, -709.0, -708.0, -40.0, -39.999, 39.999, 40.0, 700.0, 0.0, 1e-300, -1e-300]])
+    f = a.reshape(-1, 1); y = np.ones_like(f); mu = np.zeros_like(f)
+    for chunk in (slice(0, 4001), slice(4001, None)):
+        got = np.array([G.ll_bar(f[i:i + 1], y[i:i + 1], mu[i:i + 1])[0] for i in range(*chunk.indices(len(a)))][:400]) if False else None
+    # one column per value: n = 1
+    got = G.ll_bar(f.T.copy(), y.T.copy(), mu.T.copy())
+    with np.errstate(over="ignore"):
+        want = -np.log(1 + np.exp(-a))
+    finite = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), finite)          # -inf exactly where the reference overflows (a < -709.78)
+    assert np.max(np.abs(got[finite] - want[finite]) / np.maximum(1.0, np.abs(want[finite]))) <= 4e-16
+
+
 def test_ll_bar(G, O):
     prob = make_problem(300, 20, seed=3)
     rs = np.random.RandomState(1)
