@@ -13,6 +13,7 @@
 #include "gemm_f64.cuh"
 #include "kernels.cuh"
 #include "linalg.cuh"
+#include "theta_int8.cuh"
 
 namespace gpirt {
 
@@ -36,6 +37,8 @@ struct gpirt_b200_sampler {
     Comm comm;
     cudaStream_t stream = nullptr;
     CholLookahead lookahead;
+    ThetaInt8 ti8;               // tcgen05 int8 path of the theta contraction (no missing data)
+    bool use_ti8 = false;
     bool has_missing = false;
     bool timing = true;
     uint32_t sweep_counter = 0;
@@ -177,6 +180,14 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         return GPIRT_B200_ERR_Y_VALUE;
     }
     has_missing = cnt[0] != 0;
+    {   // the theta contraction runs on the int8 tensor cores when y has no missing cells (|y| = 1 everywhere)
+        const char* e = getenv("GPIRT_THETA_INT8");
+        const bool want = e ? atoi(e) != 0 : true;
+        if (want && !has_missing) {
+            GP_TRY(ti8.init(stream, y8, ldy8, n, m));
+            use_ti8 = true;
+        }
+    }
     GP_TRY(step_rebuild());                                                         // gpirtMCMC.cpp:15-17
     GP_CUDA(cudaStreamSynchronize(stream));
     return check_status();
@@ -279,7 +290,8 @@ int gpirt_b200_sampler::step_draw_theta(uint32_t sweep) {
     toc();
     tic(GPIRT_B200_T_THETA_GEMM);
     // logP^T[k,i] = 1/2 sum_j f*_kj y_ij   (y = 0 where missing)
-    GP_TRY(gemm_f64(stream, false, true, G(N, n, m, fstar, ldN, yd, ldn, logPt, ldN, 0.5, 0.0, TRI_NONE)));
+    if (use_ti8) GP_TRY(ti8.run(stream, fstar, ldN, 0.5, logPt, ldN));
+    else GP_TRY(gemm_f64(stream, false, true, G(N, n, m, fstar, ldN, yd, ldn, logPt, ldN, 0.5, 0.0, TRI_NONE)));
     const double* rs_for_draw = rowsum;
     if (has_missing) {  // - sum_j obs_ij D_kj with obs = |y|
         GP_TRY(gemm_f64(stream, false, true, G(N, n, m, Dmat, ldN, yd, ldn, logPt, ldN, -1.0, 1.0, TRI_NONE, 1)));
@@ -339,6 +351,7 @@ void gpirt_b200_sampler::destroy() {
     lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
     comm_destroy(comm);
+    ti8.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
                     kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -210,6 +210,32 @@ def test_step_draw_theta(G, O, n, m, missing):
     s.close()
 
 
+@pytest.mark.parametrize("n,m", [(130, 129), (1100, 700), (4096, 300)])
+def test_theta_int8_tensor_core_path_matches_fp64_path(G, O, n, m, monkeypatch):
+    """tcgen05 int8 (exact integer) contraction vs the FP64 DMMA contraction vs the oracle, no missing data"""
+    from gpirt_b200 import _lib
+    prob = make_problem(n, m, seed=n + m, missing=0.0, grid_theta=True)
+    rs = np.random.RandomState(7)
+    fstar = np.asfortranarray(rs.randn(1001, m).cumsum(axis=0) * 0.04 + 3.0 * rs.randn(1, m))
+    fstar[17, 3] = 0.0; fstar[500, :] *= 1e-6; fstar[900, 0] = 37.5        # zeros, tiny row, large entry
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GPIRT_THETA_INT8", flag)
+        s = G.Sampler(prob["y"], prob["theta"], seed=5)
+        s.set(_lib.FSTAR, fstar)
+        s.step(_lib.STEP_DRAW_THETA, 3)
+        out[flag] = (s.get(_lib.LOGP), s.get(_lib.THETA_IDX).astype(int))
+        s.close()
+    ts, prior = O.grid()
+    rng = O.Rng.keyed(5); rng.set_sweep(3)
+    _, idxo, logpo = O.draw_theta(ts, prob["y"], prior, fstar, rng, mode=1)
+    want = logpo - prior[None, :]
+    for flag in ("1", "0"):
+        assert np.max(np.abs(out[flag][0] - want) / np.maximum(1.0, np.abs(want))) <= 1e-12, flag
+        assert np.array_equal(out[flag][1], idxo), flag
+    assert np.max(np.abs(out["1"][0] - out["0"][0]) / np.maximum(1.0, np.abs(want))) <= 2e-13
+
+
 @pytest.mark.parametrize("n,m,missing", [(40, 12, 0.1), (100, 50, 0.05), (1100, 20, 0.0), (2500, 6, 0.1)])
 def test_step_draw_beta(G, O, n, m, missing):
     from gpirt_b200 import _lib
