@@ -243,23 +243,33 @@ def main():
     timers = s.timings()
     value = 1000.0 * K / ms
 
-    # roofline of the dominant kernel (largest share of the timed region)
+    # roofline of the dominant kernel (largest summed CUDA-event time in the timed region)
     m_loc = j1 - j0
     work = {"lz_gemm": ("tensor", float(n) * n * m_loc), "fstar_gemm": ("tensor", 2.0 * n * N_GRID * m_loc),
-            "theta_gemm": ("tensor", 2.0 * n * N_GRID * m_loc), "chol": ("tensor", n ** 3 / 3.0), "trtri": ("tensor", n ** 3 / 3.0),
+            "chol": ("tensor", n ** 3 / 3.0), "trtri": ("tensor", n ** 3 / 3.0),
             "trsm": ("tensor", 2.0 * n * n * N_GRID if args.fstar_mode == 0 else n * n * N_GRID + 2.0 * n * n * m_loc),
             "ess": ("hbm", 25.0 * n * m_loc), "beta": ("hbm", 17.0 * n * m_loc), "kbuild": ("hbm", 4.0 * n * n)}
-    tot_ms = sum(v[0] for v in timers.values()) or 1.0
     dom = max(work, key=lambda k: timers[k][0])
     bound, alg = work[dom]
-    dom_ms = timers[dom][0] / max(1, timers[dom][1])
+    dom_ms = timers[dom][0] / K                      # per sweep (a segment may be several launches, e.g. L Z in groups)
     peaks, peak_src = _peaks()
+    dmma, dfma = G.fp64_peak_tflops()
+    fp64_src = ("FP64 tensor pipe (DMMA.8x8x4) issue-rate microbenchmark measured in this run; "
+                "MEASURED_PEAKS.json has no FP64 figure")
     if bound == "tensor":
-        dmma, dfma = G.fp64_peak_tflops()
-        achieved, peak, unit = alg / dom_ms * 1e-9, dmma, "TFLOP/s"
-        peak_src = "FP64 tensor pipe (DMMA.8x8x4) issue-rate microbenchmark measured in this run; MEASURED_PEAKS.json has no FP64 figure"
+        achieved, peak, unit, peak_src = alg / dom_ms * 1e-9, dmma, "TFLOP/s", fp64_src
     else:
         achieved, peak, unit = alg / dom_ms * 1e-6, peaks["hbm_gbs"], "GB/s"
+    # the same segments timed WITHOUT sweep pipelining (no co-running kernels): kernel quality, not schedule
+    s.set_pipeline(False)
+    s.sweep(1)
+    s.timings(reset=True)
+    Ki = 3
+    ms_iso = s.sweep(Ki)
+    t_iso = s.timings()
+    s.set_pipeline(True)
+    iso_ms = t_iso[dom][0] / Ki
+    iso = alg / iso_ms * (1e-9 if bound == "tensor" else 1e-6)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tp):
@@ -269,9 +279,13 @@ def main():
         except Exception:
             traffic = None
     roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_work_per_launch": alg,
-                "avg_launch_ms": dom_ms, "share_of_step": timers[dom][0] / tot_ms,
-                "per_step_ms": {k: v[0] / K for k, v in timers.items() if v[1]}}
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_work_per_sweep": alg,
+                "ms_per_sweep": dom_ms, "share_of_step": dom_ms / (ms / K),
+                "note": "timed region runs pipelined: the L Z product and the beta step execute UNDER the Cholesky chain, so "
+                        "their event durations include co-running kernels; `isolated` repeats the measurement with pipelining off",
+                "isolated": {"achieved": iso, "frac": iso / peak, "ms_per_sweep": iso_ms, "sweep_ms_unpipelined": ms_iso / Ki},
+                "per_step_ms": {k: v[0] / K for k, v in timers.items() if v[1]},
+                "per_step_ms_isolated": {k: v[0] / Ki for k, v in t_iso.items() if v[1]}}
     s.close()
 
     line = {"metric": "gibbs_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": max(3, W),

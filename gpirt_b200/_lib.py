@@ -14,7 +14,8 @@ EXPORTS = [
     "gpirt_b200_mcmc", "gpirt_b200_strerror", "gpirt_b200_last_error", "gpirt_b200_device_count",
     "gpirt_b200_nccl_unique_id", "gpirt_b200_sampler_create", "gpirt_b200_sampler_init_draws",
     "gpirt_b200_sampler_sweep", "gpirt_b200_sampler_step", "gpirt_b200_sampler_get", "gpirt_b200_sampler_set",
-    "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_launches",
+    "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_set_pipeline",
+    "gpirt_b200_sampler_launches",
     "gpirt_b200_sampler_destroy", "gpirt_b200_se_cov", "gpirt_b200_chol_lower", "gpirt_b200_dgemm",
     "gpirt_b200_trsm_lower", "gpirt_b200_ll_bar", "gpirt_b200_fp64_peak_tflops", "gpirt_b200_rng_probe",
 ]
@@ -65,6 +66,7 @@ def load():
     L.gpirt_b200_sampler_set.argtypes = [C.c_void_p, C.c_int, _dp]
     L.gpirt_b200_sampler_timings.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int64), C.c_int]
     L.gpirt_b200_sampler_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.gpirt_b200_sampler_set_pipeline.argtypes = [C.c_void_p, C.c_int]
     L.gpirt_b200_sampler_launches.argtypes = [C.c_void_p]
     L.gpirt_b200_sampler_launches.restype = C.c_int64
     L.gpirt_b200_sampler_destroy.argtypes = [C.c_void_p]

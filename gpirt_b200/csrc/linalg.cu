@@ -427,7 +427,13 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
                     h[1]-h[0], h[2]-h[1], h[3]-h[2], h[4]-h[3], h[5]-h[4], h[6]-h[5], h[7]-h[6], h[8]-h[7], h[9]-h[8], h[9]-h[0]);
         }
         const int rem = n - k0 - nb;
-        if (rem <= 0) break;
+        if (rem <= 0) {
+            if (two && la->after_panel) {
+                GP_CUDA(cudaEventRecord(la->ev_panel[k], stream));
+                GP_TRY(la->after_panel(k, nblk, la->ev_panel[k]));
+            }
+            break;
+        }
         double* P = Akk + nb;  // rem x nb panel below the diagonal block
         GemmArgs g;            // P <- P Dinv_k^T, in place: one 128-wide column tile, each CTA rewrites only rows it read
         g.M = rem; g.N = nb; g.K = nb; g.A = P; g.lda = lda; g.B = Dinv + k0; g.ldb = ldd; g.C = P; g.ldc = lda;
@@ -443,6 +449,7 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
         }
         const int nb1 = min(CHOL_NB, rem);   // width of block column k+1
         GP_CUDA(cudaEventRecord(la->ev_panel[k], stream));
+        if (la->after_panel) GP_TRY(la->after_panel(k, nblk, la->ev_panel[k]));
         if (rem - nb1 > 0) {                 // bulk(k): columns >= k+2, on the aux stream
             GP_CUDA(cudaStreamWaitEvent(la->aux, la->ev_panel[k], 0));
             GemmArgs u;

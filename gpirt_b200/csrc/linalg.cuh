@@ -1,5 +1,6 @@
 // Blocked FP64 factorisation / triangular solves built on the DMMA GEMM (gemm_f64.cuh).
 #pragma once
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -37,6 +38,9 @@ constexpr int CHOL_NB = 128;  // panel width of the right-looking factorisation;
 struct CholLookahead {      // second stream + events for the one-panel look-ahead (owned by the caller)
     cudaStream_t aux = nullptr;
     std::vector<cudaEvent_t> ev_panel, ev_bulk;
+    // optional hook: called on the host right after block column k of L has been enqueued as final (event `done`,
+    // recorded on the main stream) — lets the caller start work that consumes finished columns while the chain runs
+    std::function<int(int k, int nblk, cudaEvent_t done)> after_panel;
 };
 int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv128, int64_t ldd, int* d_status,
                    CholLookahead* la = nullptr);

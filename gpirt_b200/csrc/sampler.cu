@@ -39,6 +39,15 @@ struct gpirt_b200_sampler {
     CholLookahead lookahead;
     ThetaInt8 ti8;               // tcgen05 int8 path of the theta contraction (no missing data)
     bool use_ti8 = false;
+    // sweep pipelining: the latency-bound Cholesky chain of sweep t overlaps (a) the beta step of sweep t, (b) the Philox
+    // fill of Z for sweep t+1 and (c) the product nu = L Z of sweep t+1, accumulated block column by block column behind
+    // the factorisation (each group of LZ_GROUP finished panels contributes nu[r0:, :] += L[r0:, r0:r1] Z[r0:r1, :])
+    bool pipeline = true;
+    static constexpr int LZ_GROUP = 4;
+    cudaStream_t st_beta = nullptr, st_lz = nullptr;
+    cudaEvent_t ev_theta = nullptr, ev_z = nullptr, ev_beta = nullptr, ev_lz = nullptr;
+    bool nu_ready = false;       // nu already holds L z for sweep nu_sweep
+    uint32_t nu_sweep = 0;
     bool has_missing = false;
     bool timing = true;
     uint32_t sweep_counter = 0;
@@ -60,6 +69,19 @@ struct gpirt_b200_sampler {
     double ms[GPIRT_B200_TIMER_COUNT] = {0};
     int64_t calls[GPIRT_B200_TIMER_COUNT] = {0};
     Seg cur{};
+
+    Seg tic_on(int timer, cudaStream_t st) {
+        Seg sg{timer, nullptr, nullptr};
+        if (!timing) return sg;
+        sg.a = get_event(); sg.b = get_event();
+        cudaEventRecord(sg.a, st);
+        return sg;
+    }
+    void toc_on(Seg& sg, cudaStream_t st) {
+        if (!timing || !sg.a) return;
+        cudaEventRecord(sg.b, st);
+        pending.push_back(sg);
+    }
 
     cudaEvent_t get_event() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -102,6 +124,8 @@ struct gpirt_b200_sampler {
     int step_draw_theta(uint32_t sweep);
     int step_draw_beta(uint32_t sweep);
     int step_rebuild();
+    int ess_only(uint32_t sweep);
+    int rebuild_pipelined(uint32_t sweep, uint32_t next_sweep);
     int sweep(int accumulate);
     int check_status();
     void destroy();
@@ -139,8 +163,17 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_TRY(comm_init(comm, opts.rank, opts.world_size, opts.nccl_unique_id));
     }
     launches_at_create = g_launch_count;
-    GP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    GP_CUDA(cudaStreamCreateWithFlags(&lookahead.aux, cudaStreamNonBlocking));
+    {   // the factorisation chain and its bulk updates run at the highest priority, the overlapped L Z product at the lowest
+        int least = 0, greatest = 0;
+        GP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        GP_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, greatest));
+        GP_CUDA(cudaStreamCreateWithPriority(&lookahead.aux, cudaStreamNonBlocking, greatest));
+        GP_CUDA(cudaStreamCreateWithPriority(&st_beta, cudaStreamNonBlocking, least));
+        GP_CUDA(cudaStreamCreateWithPriority(&st_lz, cudaStreamNonBlocking, least));
+        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        const char* pe = getenv("GPIRT_PIPELINE");
+        if (pe) pipeline = atoi(pe) != 0;
+    }
 
     const size_t nm = (size_t)ldn * m, Nm = (size_t)ldN * m;
     GP_TRY(alloc(y8, (size_t)ldy8 * m)); GP_TRY(alloc(yd, nm));
@@ -331,11 +364,75 @@ int gpirt_b200_sampler::init_draws() {
     return check_status();
 }
 
+// ESS with nu already in place (the product L z was accumulated behind the previous sweep's factorisation)
+int gpirt_b200_sampler::ess_only(uint32_t sweep) {
+    tic(GPIRT_B200_T_ESS);
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1));
+    toc();
+    return GPIRT_B200_OK;
+}
+
+// End of sweep `sweep` with the next sweep's proposals prepared under the factorisation:
+//   st_beta : Z(next) = Philox normals, then the beta step                                   (needs the new theta only)
+//   stream  : K(theta,theta)+1e-3 I, right-looking Cholesky chain (+ its bulk stream), L^-1
+//   st_lz   : after every LZ_GROUP finished block columns  nu[r0:, :] (+)= L[r0:, r0:r1] Z[r0:r1, :]
+int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
+    GP_CUDA(cudaEventRecord(ev_theta, stream));
+    GP_CUDA(cudaStreamWaitEvent(st_beta, ev_theta, 0));
+    {
+        Seg sg = tic_on(GPIRT_B200_T_FILL_Z, st_beta);
+        GP_TRY(launch_fill_normal(st_beta, Z, n, m, ldn, key_at(next_sweep), P_ESS_Z, item_offset));
+        toc_on(sg, st_beta);
+        GP_CUDA(cudaEventRecord(ev_z, st_beta));
+        Seg sb = tic_on(GPIRT_B200_T_BETA, st_beta);
+        GP_TRY(launch_beta(st_beta, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1));
+        toc_on(sb, st_beta);
+        GP_CUDA(cudaEventRecord(ev_beta, st_beta));
+    }
+    tic(GPIRT_B200_T_KBUILD);
+    GP_TRY(launch_se_cov(stream, theta, n, theta, n, 0.001, true, L, ldn));
+    toc();
+    bool first = true;
+    lookahead.after_panel = [&](int k, int nblk, cudaEvent_t done) -> int {
+        if ((k + 1) % LZ_GROUP != 0 && k != nblk - 1) return GPIRT_B200_OK;
+        const int g = k / LZ_GROUP;
+        const int r0 = g * LZ_GROUP * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
+        if (first) { GP_CUDA(cudaStreamWaitEvent(st_lz, ev_z, 0)); first = false; }
+        GP_CUDA(cudaStreamWaitEvent(st_lz, done, 0));
+        Seg sg = tic_on(GPIRT_B200_T_LZ_GEMM, st_lz);
+        GemmArgs a;
+        a.M = n - r0; a.N = m; a.K = r1 - r0;
+        a.A = L + r0 + (int64_t)r0 * ldn; a.lda = ldn; a.B = Z + r0; a.ldb = ldn; a.C = nu + r0; a.ldc = ldn;
+        a.alpha = 1.0; a.beta = (g == 0) ? 0.0 : 1.0; a.tri = TRI_A_LOWER;
+        GP_TRY(gemm_f64(st_lz, false, false, a));
+        toc_on(sg, st_lz);
+        if (k == nblk - 1) GP_CUDA(cudaEventRecord(ev_lz, st_lz));
+        return GPIRT_B200_OK;
+    };
+    tic(GPIRT_B200_T_CHOL);
+    int rc = potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, &lookahead);
+    lookahead.after_panel = nullptr;
+    GP_TRY(rc);
+    toc();
+    tic(GPIRT_B200_T_TRTRI);
+    GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
+    toc();
+    GP_CUDA(cudaStreamWaitEvent(stream, ev_lz, 0));
+    GP_CUDA(cudaStreamWaitEvent(stream, ev_beta, 0));
+    nu_ready = true;
+    nu_sweep = next_sweep;
+    return GPIRT_B200_OK;
+}
+
 int gpirt_b200_sampler::sweep(int accumulate) {
     const uint32_t t = ++sweep_counter;
-    GP_TRY(step_draw_f(t));
+    const bool can_pipe = pipeline && ceil_div(n, CHOL_NB) > 2;   // the look-ahead factorisation needs > 2 panels
+    if (can_pipe && nu_ready && nu_sweep == t) GP_TRY(ess_only(t));
+    else GP_TRY(step_draw_f(t));
+    nu_ready = false;
     GP_TRY(step_draw_fstar(t, accumulate));
     GP_TRY(step_draw_theta(t));
+    if (can_pipe) return rebuild_pipelined(t, t + 1);
     GP_TRY(step_draw_beta(t));
     GP_TRY(step_rebuild());   // mu = X beta and mu* = X* beta (gpirtMCMC.cpp:74-75) are never materialised
     return GPIRT_B200_OK;
@@ -350,6 +447,8 @@ void gpirt_b200_sampler::destroy() {
     for (auto e : lookahead.ev_bulk) cudaEventDestroy(e);
     lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
+    for (cudaStream_t* q : {&st_beta, &st_lz}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
+    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
@@ -492,6 +591,7 @@ int gpirt_b200_sampler_sweep(gpirt_b200_sampler* s, int n_sweeps, int accumulate
 
 int gpirt_b200_sampler_step(gpirt_b200_sampler* s, int step, uint32_t sweep) {
     if (!s) return GPIRT_B200_ERR_ARG;
+    s->nu_ready = false;
     int rc;
     switch (step) {
         case GPIRT_B200_STEP_DRAW_F: rc = s->step_draw_f(sweep); break;
@@ -554,6 +654,7 @@ int gpirt_b200_sampler_set(gpirt_b200_sampler* s, int field, const double* host_
     if (!s || !host_in) return GPIRT_B200_ERR_ARG;
     double* dev; int64_t ld; int rows, cols;
     if (field_shape(s, field, &dev, &ld, &rows, &cols)) return GPIRT_B200_ERR_ARG;
+    s->nu_ready = false;
     GP_TRY(upload_padded(dev, ld, host_in, rows, cols, s->stream));
     GP_CUDA(cudaStreamSynchronize(s->stream));
     return GPIRT_B200_OK;
@@ -572,6 +673,13 @@ int gpirt_b200_sampler_timings(gpirt_b200_sampler* s, double* ms, int64_t* calls
 int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->timing = enabled != 0;
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled) {
+    if (!s) return GPIRT_B200_ERR_ARG;
+    s->pipeline = enabled != 0;
+    s->nu_ready = false;
     return GPIRT_B200_OK;
 }
 

@@ -135,6 +135,9 @@ class Sampler:
     def set_timing(self, on):
         _lib.check(_lib.load().gpirt_b200_sampler_set_timing(self.h, int(on)))
 
+    def set_pipeline(self, on):
+        _lib.check(_lib.load().gpirt_b200_sampler_set_pipeline(self.h, int(on)))
+
     def timings(self, reset=False):
         ms = np.zeros(len(_lib.TIMER_NAMES))
         calls = np.zeros(len(_lib.TIMER_NAMES), dtype=np.int64)

@@ -120,6 +120,9 @@ enum gpirt_b200_timer {
 };
 int gpirt_b200_sampler_timings(gpirt_b200_sampler* s, double* ms, int64_t* calls, int reset);
 int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled); /* per-step events on (default) / off */
+/* sweep pipelining on (default) / off: on, the Cholesky chain of a sweep overlaps its beta step and the next sweep's
+ * Z fill and L Z product (identical draws either way; off gives un-overlapped per-kernel timings) */
+int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled);
 int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s); /* kernels launched by this sampler so far */
 void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s);
 
