@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--fstar-mode", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -320,6 +321,25 @@ def main():
                        "note": "gpirtMCMC(sample_iterations=%d, burn_iterations=0) wall time incl. setup, initial draws, H2D of y "
                                "and D2H of every theta/beta/f draw (reference output contract)" % Ke}
         del out
+
+    # ------------------------------------------------------------------ the other single-GPU configs, briefly (N = 1 only)
+    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_extras:
+        extras = {}
+        for wl in ("c1", "c2"):
+            try:
+                c = synthetic.WORKLOADS[wl]
+                d2 = synthetic.make(c["n"], c["m"])
+                s2 = G.Sampler(d2["y"], d2["theta_init"], d2["pm"], d2["psd"], d2["pstep"], seed=synthetic.SEED, device=local_rank)
+                s2.set_timing(False)
+                s2.init_draws()
+                s2.sweep(5)
+                k2 = 50
+                ms2 = s2.sweep(k2)
+                extras[wl] = {"n": c["n"], "m": c["m"], "value": 1000.0 * k2 / ms2, "unit": "sweeps/s", "ms_per_step": ms2 / k2, "steps": k2}
+                s2.close()
+            except Exception as ex:
+                extras[wl] = {"error": repr(ex)}
+        line["other_workloads"] = extras
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -205,15 +205,28 @@ __device__ __forceinline__ double fast_rcp(double p) {
 //   W_ij -= (a_ic / p_c) W_cj ,  W_ic = -(a_ic / p_c)  (i > c >= j;  W accumulates Lh^-1, W_cc = 1 implicit)
 // and afterwards  L = Lh D^1/2 : l_ij = a_ij / sqrt(p_j),   X = L^-1 = D^-1/2 W : x_ij = W_ij / sqrt(p_i).
 // W_ij lives transposed at S[j][i] (strict upper triangle), pivots in pv[].
+__device__ long long* g_dbg_ptr = nullptr;
 __device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o, int tid, int* status) {
+    long long* dbg = g_dbg_ptr;
     const int j = tid & 31, i0 = tid >> 5;   // column j, rows i0 and i0 + 16
     bool bad = false;
+    // The pivot of step c+1 is known from data that is final when step c starts,
+    //   p_{c+1} = a_{c+1,c+1} - a_{c+1,c}^2 / p_c ,
+    // so every thread computes it (and its reciprocal) redundantly DURING step c: the long reciprocal chain overlaps
+    // the update chain instead of heading the next step.
+    double p = S[o * DLD + o];
+    double pinv = fast_rcp(p);
     for (int c = 0; c < 32; ++c) {
         const int cc = o + c;
-        const double p = S[cc * DLD + cc];
         bad |= !(p > 0.0);
-        const double pinv = fast_rcp(p);
+        if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[10 + (tid ? 4 : 0)] = clock64();
         if (tid == 0) pv[cc] = p;
+        double p_next = 1.0, pinv_next = 1.0;
+        if (c + 1 < 32) {
+            const double a = S[(cc + 1) * DLD + cc];
+            p_next = fma(-(a * pinv), a, S[(cc + 1) * DLD + cc + 1]);
+            pinv_next = fast_rcp(p_next);
+        }
         // one predicated path for all lanes (no divergence): j > c updates A(i,j); j <= c updates W(i,j) stored at
         // S[j][i], where j == c is the fresh column W(i,c) = 0 - mlt * 1 (the strict upper triangle starts as zeros)
         const double other = (j == c) ? 1.0 : S[(o + j) * DLD + cc];   // a_jc, or W(c,j) which lives at S[o+j][o+c]
@@ -225,7 +238,10 @@ __device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o
             const bool active = (i > c) && (j <= c || i >= j);
             if (active) *tgt = fma(-mlt, other, *tgt);
         }
+        if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[11 + (tid ? 4 : 0)] = clock64();
         __syncthreads();
+        if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[12 + (tid ? 4 : 0)] = clock64();
+        p = p_next; pinv = pinv_next;
     }
     if (bad && tid == 0) atomicExch(status, 1);   // not positive definite (or NaN)
     // scale: l_ij = a_ij rsqrt(p_j) (i > j);  x_ij = W_ij rsqrt(p_i), stored at S[j][i];  diagonals
@@ -348,6 +364,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A,
     double* pv = ldiag + DB;
     const int tid = threadIdx.x;
     DIAG_MARK(0);
+    if (tid == 0) g_dbg_ptr = dbg;
+    __syncthreads();
     // load the lower triangle (rows/cols >= nb padded with the identity)
     for (int idx = tid; idx < DB * DB; idx += DTHREADS) {
         const int r = idx % DB, c = idx / DB;
@@ -416,15 +434,17 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
         double* Akk = A + (int64_t)k0 * (lda + 1);
         static long long* dbg = nullptr;
         static bool dbg_on = getenv("GPIRT_DIAG_DEBUG") != nullptr;
-        if (dbg_on && !dbg) cudaMalloc((void**)&dbg, 16 * sizeof(long long));
+        if (dbg_on && !dbg) cudaMalloc((void**)&dbg, 32 * sizeof(long long));
         GP_LAUNCH(k_diag128, 1, DTHREADS, smem, stream, Akk, lda, nb, Dinv + k0, ldd, d_status, dbg_on ? dbg : nullptr);
         GP_CUDA(cudaGetLastError());
         if (dbg_on && k == 1) {
-            long long h[16];
+            long long h[32];
             cudaStreamSynchronize(stream);
             cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "k_diag128 phases (cycles): load %lld | diag32 %lld | panel+syrk32 %lld | diag32+inv32 %lld | panel64 %lld | syrk64 %lld | f_i_64 %lld | inv64 %lld | store %lld | total %lld\n",
                     h[1]-h[0], h[2]-h[1], h[3]-h[2], h[4]-h[3], h[5]-h[4], h[6]-h[5], h[7]-h[6], h[8]-h[7], h[9]-h[8], h[9]-h[0]);
+            fprintf(stderr, "step c=8: warp0 work %lld barrier %lld | warp15 work %lld barrier %lld | skew start %lld\n",
+                    h[11]-h[10], h[12]-h[11], h[15]-h[14], h[16]-h[15], h[14]-h[10]);
         }
         const int rem = n - k0 - nb;
         if (rem <= 0) {

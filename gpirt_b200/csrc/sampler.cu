@@ -48,6 +48,9 @@ struct gpirt_b200_sampler {
     cudaEvent_t ev_theta = nullptr, ev_z = nullptr, ev_beta = nullptr, ev_lz = nullptr;
     bool nu_ready = false;       // nu already holds L z for sweep nu_sweep
     uint32_t nu_sweep = 0;
+    bool solve_ready = false;    // kstar already holds S^-1 K* and s the predictive sd for the current theta (ev_solve)
+    cudaEvent_t ev_linv = nullptr, ev_solve = nullptr;
+    int fstar_solves(cudaStream_t st);
     bool has_missing = false;
     bool timing = true;
     uint32_t sweep_counter = 0;
@@ -170,7 +173,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_CUDA(cudaStreamCreateWithPriority(&lookahead.aux, cudaStreamNonBlocking, greatest));
         GP_CUDA(cudaStreamCreateWithPriority(&st_beta, cudaStreamNonBlocking, least));
         GP_CUDA(cudaStreamCreateWithPriority(&st_lz, cudaStreamNonBlocking, least));
-        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         const char* pe = getenv("GPIRT_PIPELINE");
         if (pe) pipeline = atoi(pe) != 0;
     }
@@ -274,25 +277,41 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
     return GPIRT_B200_OK;
 }
 
+// The item-independent part of draw_fstar (draw-fstar.cpp:17-20): kstar = K(theta, theta*), tmp = L^-1 kstar,
+// s = 1 - sqrt(colsum(tmp % tmp)), and A = L^-T tmp so that K*^T L^-T L^-1 f_j = A^T f_j needs one product per sweep
+// instead of two solves per item.  Depends on theta and L only, so the pipelined sweep runs it beside the ESS.
+int gpirt_b200_sampler::fstar_solves(cudaStream_t st) {
+    const int N = N_GRID;
+    Seg a = tic_on(GPIRT_B200_T_KSTAR, st);
+    GP_TRY(launch_se_cov(st, theta, n, theta_star, N, 0.0, false, kstar, ldn));              // :17
+    toc_on(a, st);
+    Seg b = tic_on(GPIRT_B200_T_TRSM, st);
+    GP_TRY(gemm_f64(st, false, false, G(n, N, n, Linv, ldn, kstar, ldn, kstar2, ldn, 1.0, 0.0, TRI_A_LOWER)));   // :19
+    GP_TRY(launch_fstar_sd(st, kstar2, ldn, n, N, s));                                        // :20
+    GP_TRY(gemm_f64(st, true, false, G(n, N, n, Linv, ldn, kstar2, ldn, kstar, ldn, 1.0, 0.0, TRI_A_UPPER)));
+    toc_on(b, st);
+    return GPIRT_B200_OK;
+}
+
 // f_star = draw_fstar(f, theta, theta_star, cholS, mu_star)                         gpirtMCMC.cpp:69, draw-fstar.cpp:10-31
 int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
     const RngKey k = key_at(sweep);
     const int N = N_GRID;
-    tic(GPIRT_B200_T_KSTAR);
-    GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));          // :17
-    toc();
-    tic(GPIRT_B200_T_TRSM);
-    // tmp = solve(trimatl(L), kstar) as the triangular product L^-1 K*                      :19
-    GP_TRY(gemm_f64(stream, false, false, G(n, N, n, Linv, ldn, kstar, ldn, kstar2, ldn, 1.0, 0.0, TRI_A_LOWER)));
-    GP_TRY(launch_fstar_sd(stream, kstar2, ldn, n, N, s));                                   // :20
     if (opts.fstar_mode == 0) {
-        // K*^T L^-T L^-1 f_j = (L^-T tmp)^T f_j : one n x 1001 product instead of two solves per item
-        GP_TRY(gemm_f64(stream, true, false, G(n, N, n, Linv, ldn, kstar2, ldn, kstar, ldn, 1.0, 0.0, TRI_A_UPPER)));
-        toc();
+        if (solve_ready) GP_CUDA(cudaStreamWaitEvent(stream, ev_solve, 0));   // done under the previous sweep's tail / this sweep's ESS
+        else GP_TRY(fstar_solves(stream));
+        solve_ready = false;
         tic(GPIRT_B200_T_FSTAR_GEMM);
         GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, f, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
         toc();
     } else {
+        solve_ready = false;
+        tic(GPIRT_B200_T_KSTAR);
+        GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));          // :17
+        toc();
+        tic(GPIRT_B200_T_TRSM);
+        GP_TRY(gemm_f64(stream, false, false, G(n, N, n, Linv, ldn, kstar, ldn, kstar2, ldn, 1.0, 0.0, TRI_A_LOWER)));   // :19
+        GP_TRY(launch_fstar_sd(stream, kstar2, ldn, n, N, s));                                   // :20
         // literal: alpha_j = L^-T (L^-1 f_j) for every item (:3-8,:24), mean_j = K*^T alpha_j (:25)
         GP_TRY(gemm_f64(stream, false, false, G(n, m, n, Linv, ldn, f, ldn, Z, ldn, 1.0, 0.0, TRI_A_LOWER)));
         GP_TRY(gemm_f64(stream, true, false, G(n, m, n, Linv, ldn, Z, ldn, nu, ldn, 1.0, 0.0, TRI_A_UPPER)));
@@ -421,6 +440,13 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     GP_CUDA(cudaStreamWaitEvent(stream, ev_beta, 0));
     nu_ready = true;
     nu_sweep = next_sweep;
+    if (opts.fstar_mode == 0) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
+        GP_CUDA(cudaEventRecord(ev_linv, stream));
+        GP_CUDA(cudaStreamWaitEvent(st_lz, ev_linv, 0));
+        GP_TRY(fstar_solves(st_lz));
+        GP_CUDA(cudaEventRecord(ev_solve, st_lz));
+        solve_ready = true;
+    }
     return GPIRT_B200_OK;
 }
 
@@ -448,7 +474,7 @@ void gpirt_b200_sampler::destroy() {
     lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
     for (cudaStream_t* q : {&st_beta, &st_lz}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
-    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
@@ -592,6 +618,7 @@ int gpirt_b200_sampler_sweep(gpirt_b200_sampler* s, int n_sweeps, int accumulate
 int gpirt_b200_sampler_step(gpirt_b200_sampler* s, int step, uint32_t sweep) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->nu_ready = false;
+    if (s->solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = false; }
     int rc;
     switch (step) {
         case GPIRT_B200_STEP_DRAW_F: rc = s->step_draw_f(sweep); break;
@@ -655,6 +682,7 @@ int gpirt_b200_sampler_set(gpirt_b200_sampler* s, int field, const double* host_
     double* dev; int64_t ld; int rows, cols;
     if (field_shape(s, field, &dev, &ld, &rows, &cols)) return GPIRT_B200_ERR_ARG;
     s->nu_ready = false;
+    if (s->solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = false; }
     GP_TRY(upload_padded(dev, ld, host_in, rows, cols, s->stream));
     GP_CUDA(cudaStreamSynchronize(s->stream));
     return GPIRT_B200_OK;
@@ -680,6 +708,7 @@ int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->pipeline = enabled != 0;
     s->nu_ready = false;
+    if (s->solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = false; }
     return GPIRT_B200_OK;
 }
 
