@@ -210,23 +210,13 @@ __device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o
     long long* dbg = g_dbg_ptr;
     const int j = tid & 31, i0 = tid >> 5;   // column j, rows i0 and i0 + 16
     bool bad = false;
-    // The pivot of step c+1 is known from data that is final when step c starts,
-    //   p_{c+1} = a_{c+1,c+1} - a_{c+1,c}^2 / p_c ,
-    // so every thread computes it (and its reciprocal) redundantly DURING step c: the long reciprocal chain overlaps
-    // the update chain instead of heading the next step.
-    double p = S[o * DLD + o];
-    double pinv = fast_rcp(p);
     for (int c = 0; c < 32; ++c) {
         const int cc = o + c;
+        // (computing the next pivot one step ahead would read S[c+1][c+1] while its owner updates it: keep it simple)
+        const double p = S[cc * DLD + cc];
         bad |= !(p > 0.0);
-        if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[10 + (tid ? 4 : 0)] = clock64();
+        const double pinv = fast_rcp(p);
         if (tid == 0) pv[cc] = p;
-        double p_next = 1.0, pinv_next = 1.0;
-        if (c + 1 < 32) {
-            const double a = S[(cc + 1) * DLD + cc];
-            p_next = fma(-(a * pinv), a, S[(cc + 1) * DLD + cc + 1]);
-            pinv_next = fast_rcp(p_next);
-        }
         // one predicated path for all lanes (no divergence): j > c updates A(i,j); j <= c updates W(i,j) stored at
         // S[j][i], where j == c is the fresh column W(i,c) = 0 - mlt * 1 (the strict upper triangle starts as zeros)
         const double other = (j == c) ? 1.0 : S[(o + j) * DLD + cc];   // a_jc, or W(c,j) which lives at S[o+j][o+c]
@@ -241,7 +231,6 @@ __device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o
         if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[11 + (tid ? 4 : 0)] = clock64();
         __syncthreads();
         if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[12 + (tid ? 4 : 0)] = clock64();
-        p = p_next; pinv = pinv_next;
     }
     if (bad && tid == 0) atomicExch(status, 1);   // not positive definite (or NaN)
     // scale: l_ij = a_ij rsqrt(p_j) (i > j);  x_ij = W_ij rsqrt(p_i), stored at S[j][i];  diagonals

@@ -396,6 +396,10 @@ int gpirt_b200_sampler::ess_only(uint32_t sweep) {
 //   stream  : K(theta,theta)+1e-3 I, right-looking Cholesky chain (+ its bulk stream), L^-1
 //   st_lz   : after every LZ_GROUP finished block columns  nu[r0:, :] (+)= L[r0:, r0:r1] Z[r0:r1, :]
 int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
+    static const int mask = getenv("GPIRT_PIPE_MASK") ? atoi(getenv("GPIRT_PIPE_MASK")) : 7;   // debugging: 1 LZ, 2 beta/fill, 4 solves
+    cudaStream_t st_beta = (mask & 2) ? this->st_beta : stream;
+    cudaStream_t st_lz = (mask & 1) ? this->st_lz : stream;
+    cudaStream_t st_solve = (mask & 4) ? this->st_lz : stream;
     GP_CUDA(cudaEventRecord(ev_theta, stream));
     GP_CUDA(cudaStreamWaitEvent(st_beta, ev_theta, 0));
     {
@@ -442,9 +446,9 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     nu_sweep = next_sweep;
     if (opts.fstar_mode == 0) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
         GP_CUDA(cudaEventRecord(ev_linv, stream));
-        GP_CUDA(cudaStreamWaitEvent(st_lz, ev_linv, 0));
-        GP_TRY(fstar_solves(st_lz));
-        GP_CUDA(cudaEventRecord(ev_solve, st_lz));
+        GP_CUDA(cudaStreamWaitEvent(st_solve, ev_linv, 0));
+        GP_TRY(fstar_solves(st_solve));
+        GP_CUDA(cudaEventRecord(ev_solve, st_solve));
         solve_ready = true;
     }
     return GPIRT_B200_OK;

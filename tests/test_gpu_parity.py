@@ -94,6 +94,16 @@ def test_chol_lower(G, O, n):
     assert np.max(np.abs(L - Lo)) <= 1e-9
 
 
+def test_chol_repeatable_under_load(G, O):
+    """the single-CTA diagonal-block kernel is barrier-heavy: repeat it many times and demand bitwise-identical factors"""
+    prob = make_problem(384, 2, seed=5, grid_theta=True)
+    S = O.K(prob["theta"], prob["theta"]) + 1e-3 * np.eye(384)
+    ref = G.chol_lower(S)
+    assert np.isfinite(ref).all()
+    for _ in range(150):
+        assert np.array_equal(G.chol_lower(S), ref)
+
+
 def test_chol_not_pd(G):
     from gpirt_b200._lib import GpirtError, ERR_NOT_PD
     S = np.ones((70, 70))                                  # rank one, no jitter -> chol(): decomposition failed
@@ -127,7 +137,7 @@ def test_ll_bar_extremes(G, O):
         want = -np.log(1 + np.exp(-a))
     finite = np.isfinite(want)
     assert np.array_equal(np.isfinite(got), finite)          # -inf exactly where the reference overflows (a < -709.78)
-    assert np.max(np.abs(got[finite] - want[finite]) / np.maximum(1.0, np.abs(want[finite]))) <= 4e-16
+    assert np.max(np.abs(got[finite] - want[finite]) / np.maximum(1.0, np.abs(want[finite]))) <= 1e-15
 
 
 def test_ll_bar(G, O):
