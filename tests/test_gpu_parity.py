@@ -301,6 +301,31 @@ def test_senate116_short_chain(G, O):
     assert np.max(np.abs(got["IRFs"] - want["IRFs"])) <= 1e-7
 
 
+@pytest.mark.parametrize("name", ["tiny_8x5", "small_100x37", "odd_257x12"])
+def test_golden_chains_from_the_compiled_reference(G, name):
+    """CUDA sampler vs the committed outputs of the reference's OWN sources (tests/golden/make_golden.py), same seed"""
+    import os
+    from gpirt_b200 import ResponseMatrix
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    got = G.gpirtMCMC(ResponseMatrix(g["y"]), int(g["S"]), int(g["B"]), theta_init=g["theta_init"], seed=int(g["seed"]))
+    assert np.array_equal(got["theta"], g["theta"]), "theta draws (grid points) identical to the reference"
+    assert np.max(np.abs(got["beta"] - g["beta"])) <= 1e-9
+    assert np.max(np.abs(got["f"] - g["f"])) <= 1e-7
+    assert np.max(np.abs(got["IRFs"] - g["IRFs"])) <= 1e-7
+
+
+def test_golden_senate116_from_the_compiled_reference(G):
+    import os
+    from gpirt_b200 import ResponseMatrix
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "senate116_100x418.npz"))
+    y = g["y_int8"].astype(np.float64); y[y == 0] = np.nan
+    got = G.gpirtMCMC(ResponseMatrix(y), int(g["S"]), int(g["B"]), theta_init=g["theta_init"], seed=int(g["seed"]))
+    assert np.array_equal(got["theta"], g["theta"])
+    assert np.max(np.abs(got["beta"] - g["beta"])) <= 1e-9
+    assert np.max(np.abs(got["f"][:, :, -1] - g["f_last"])) <= 1e-7
+    assert np.max(np.abs(got["IRFs"][::10] - g["IRFs_every10"])) <= 1e-7
+
+
 def test_interrupt_and_bad_y(G):
     from gpirt_b200._lib import GpirtError, ERR_INTERRUPT, ERR_Y_VALUE
     prob = make_problem(20, 6, seed=1)
