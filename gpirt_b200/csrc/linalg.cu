@@ -444,9 +444,17 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
             break;
         }
         double* P = Akk + nb;  // rem x nb panel below the diagonal block
-        GemmArgs g;            // P <- P Dinv_k^T, in place: one 128-wide column tile, each CTA rewrites only rows it read
+        GemmArgs g;            // P <- P Dinv_k^T
         g.M = rem; g.N = nb; g.K = nb; g.A = P; g.lda = lda; g.B = Dinv + k0; g.ldb = ldd; g.C = P; g.ldc = lda;
-        g.force_big = 1;
+        if (la && la->panel_scratch) {
+            // the panel step sits on the critical path: read the source from a scratch copy so the product can use
+            // the small tiles (4x the CTAs of the one-tile-wide in-place form, which must keep N in a single tile)
+            GP_CUDA(cudaMemcpy2DAsync(la->panel_scratch, (size_t)la->ld_scratch * sizeof(double), P, (size_t)lda * sizeof(double),
+                                      (size_t)rem * sizeof(double), (size_t)nb, cudaMemcpyDeviceToDevice, stream));
+            g.A = la->panel_scratch; g.lda = la->ld_scratch;
+        } else {
+            g.force_big = 1;   // in place: one 128-wide column tile, each CTA rewrites only rows it read
+        }
         GP_TRY(gemm_f64(stream, false, true, g));
         double* A22 = Akk + (int64_t)nb * (lda + 1);
         if (!two) {

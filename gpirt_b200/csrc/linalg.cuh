@@ -41,6 +41,8 @@ struct CholLookahead {      // second stream + events for the one-panel look-ahe
     // optional hook: called on the host right after block column k of L has been enqueued as final (event `done`,
     // recorded on the main stream) — lets the caller start work that consumes finished columns while the chain runs
     std::function<int(int k, int nblk, cudaEvent_t done)> after_panel;
+    double* panel_scratch = nullptr;   // optional n x 128 buffer (ld_scratch): lets the panel product leave the in-place form
+    int64_t ld_scratch = 0;
 };
 int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv128, int64_t ldd, int* d_status,
                    CholLookahead* la = nullptr);

@@ -60,7 +60,7 @@ struct gpirt_b200_sampler {
     double *yd = nullptr, *theta = nullptr, *theta_star = nullptr, *prior = nullptr, *beta = nullptr, *pm = nullptr,
            *psd = nullptr, *pstep = nullptr, *L = nullptr, *Dinv = nullptr, *f = nullptr, *Z = nullptr, *nu = nullptr,
            *fstar = nullptr, *Dmat = nullptr, *irf_sum = nullptr, *kstar = nullptr, *s = nullptr, *logPt = nullptr,
-           *partial = nullptr, *Linv = nullptr, *Tmp = nullptr, *kstar2 = nullptr;
+           *partial = nullptr, *Linv = nullptr, *Tmp = nullptr, *kstar2 = nullptr, *panel_scratch = nullptr;
     int *nprop = nullptr, *theta_idx = nullptr, *status = nullptr;  // status[0] chol, [1] ess, [2] theta-degenerate count
     unsigned long long* counters = nullptr;                        // [0] missing cells, [1] illegal cells
     static constexpr int N_CHUNKS = 32;
@@ -184,6 +184,8 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
     GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * CHOL_NB));
     GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * N_GRID));
+    GP_TRY(alloc(panel_scratch, (size_t)ldn * CHOL_NB));
+    lookahead.panel_scratch = panel_scratch; lookahead.ld_scratch = ldn;
     GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
     GP_TRY(alloc(kstar, (size_t)ldn * N_GRID)); GP_TRY(alloc(s, (size_t)ldN));
@@ -482,7 +484,7 @@ void gpirt_b200_sampler::destroy() {
     comm_destroy(comm);
     ti8.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
-                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2};
+                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, panel_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;

@@ -263,9 +263,10 @@ def test_step_draw_beta(G, O, n, m, missing):
 # ---------------------------------------------------------------------------------------------------------------------
 # lock-step chains: the whole sampler against the oracle's gpirtMCMC restatement, same seed
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,m,S,B,mode", [(30, 10, 3, 2, 0), (30, 10, 3, 2, 1), (100, 40, 2, 1, 0), (257, 33, 2, 0, 0)])
+@pytest.mark.parametrize("n,m,S,B,mode", [(2, 1, 1, 1, 0), (5, 3, 2, 0, 0), (30, 10, 3, 2, 0), (30, 10, 3, 2, 1), (100, 40, 2, 1, 0),
+                                          (257, 33, 2, 0, 0), (400, 150, 3, 1, 0), (400, 150, 2, 1, 1)])
 def test_lockstep_chain(G, O, n, m, S, B, mode):
-    prob = make_problem(n, m, seed=n + 11, missing=0.08)
+    prob = make_problem(n, m, seed=n + 11, missing=0.08 if n != 400 else 0.0)   # n = 400: pipelined sweep + int8 theta path
     seed = 4242 + n
     from gpirt_b200 import ResponseMatrix
     got = G.gpirtMCMC(ResponseMatrix(prob["y"]), S, B, beta_prior_means=prob["pm"], beta_prior_sds=prob["psd"],
