@@ -12,6 +12,7 @@ N_GRID = 1001
 # every symbol include/gpirt_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
     "gpirt_b200_mcmc", "gpirt_b200_strerror", "gpirt_b200_last_error", "gpirt_b200_device_count",
+    "gpirt_b200_release_memory",
     "gpirt_b200_nccl_unique_id", "gpirt_b200_sampler_create", "gpirt_b200_sampler_init_draws",
     "gpirt_b200_sampler_sweep", "gpirt_b200_sampler_step", "gpirt_b200_sampler_get", "gpirt_b200_sampler_set",
     "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_set_pipeline",

@@ -33,6 +33,11 @@ void set_last_error(const char* fmt, ...);
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
+// Device memory comes from the stream-ordered pool (cudaMallocAsync) with the release threshold lifted, so a second
+// gpirtMCMC() call in the same process re-uses the first call's memory instead of paying cudaMalloc / cudaFree again.
+int pool_alloc(void** p, size_t bytes, cudaStream_t st);
+void pool_free(void* p, cudaStream_t st);
+
 // launch counter (gpu_launches in bench.py): every kernel launch in this library goes through GP_LAUNCH
 extern int64_t g_launch_count;
 #define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \

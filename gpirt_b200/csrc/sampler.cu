@@ -24,6 +24,28 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_last_error; }
 
+int pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured[dev] = true;
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 256, st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return GPIRT_B200_ERR_NOMEM;
+    }
+    return GPIRT_B200_OK;
+}
+void pool_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
 }  // namespace gpirt
 
 using namespace gpirt;
@@ -113,8 +135,7 @@ struct gpirt_b200_sampler {
 
     template <typename T> int alloc(T*& p, size_t count) {
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
-        if (e != cudaSuccess) { set_last_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return GPIRT_B200_ERR_NOMEM; }
+        GP_TRY(pool_alloc(&q, count * sizeof(T) + 256, stream));
         p = (T*)q;
         return GPIRT_B200_OK;
     }
@@ -485,7 +506,8 @@ void gpirt_b200_sampler::destroy() {
     ti8.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
                     kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, panel_scratch};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) pool_free(p, stream);
+    if (stream) cudaStreamSynchronize(stream);
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
 }
@@ -583,6 +605,16 @@ const char* gpirt_b200_strerror(int status) {
     }
 }
 const char* gpirt_b200_last_error(void) { return gpirt::last_error(); }
+
+int gpirt_b200_release_memory(void) {
+    int dev = 0;
+    GP_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    GP_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    GP_CUDA(cudaDeviceSynchronize());
+    GP_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return GPIRT_B200_OK;
+}
 
 int gpirt_b200_device_count(void) {
     int n = 0;
@@ -752,7 +784,7 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
         gpirt_b200_sampler* s; cudaStream_t copy; cudaEvent_t ev[2]; double* snap_f[2]; double* snap_small[2];
         ~Guard() {
             if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
-            for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); if (snap_f[i]) cudaFree(snap_f[i]); if (snap_small[i]) cudaFree(snap_small[i]); }
+            for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); pool_free(snap_f[i], s->stream); pool_free(snap_small[i], s->stream); }
             gpirt_b200_sampler_destroy(s);
         }
     } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -762,8 +794,8 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     GP_CUDA(cudaStreamCreateWithFlags(&gd.copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         GP_CUDA(cudaEventCreateWithFlags(&gd.ev[i], cudaEventDisableTiming));
-        GP_CUDA(cudaMalloc((void**)&gd.snap_small[i], small.size() * sizeof(double)));
-        if (keep_f) GP_CUDA(cudaMalloc((void**)&gd.snap_f[i], nm * sizeof(double)));
+        GP_TRY(pool_alloc((void**)&gd.snap_small[i], small.size() * sizeof(double), s->stream));
+        if (keep_f) GP_TRY(pool_alloc((void**)&gd.snap_f[i], nm * sizeof(double), s->stream));
     }
     double t_c = now();
     int rc = s->init_draws();

@@ -269,11 +269,12 @@ int ThetaInt8::init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n_, int 
     m_pad = round_up(m, TI_BK);
     n_pad = round_up(n, TI_BM);
     c_pad = round_up((int64_t)8 * N_GRID, TI_BN);
-    GP_CUDA(cudaMalloc((void**)&yt, (size_t)n_pad * m_pad));
-    GP_CUDA(cudaMalloc((void**)&Q, (size_t)c_pad * m_pad));
-    GP_CUDA(cudaMalloc((void**)&partial, (size_t)N_CHUNKS * N_GRID * sizeof(double)));
-    GP_CUDA(cudaMalloc((void**)&qscale, (size_t)N_GRID * sizeof(double)));
-    GP_CUDA(cudaMalloc((void**)&oscale, (size_t)N_GRID * sizeof(double)));
+    GP_TRY(pool_alloc((void**)&yt, (size_t)n_pad * m_pad, st));
+    GP_TRY(pool_alloc((void**)&Q, (size_t)c_pad * m_pad, st));
+    GP_TRY(pool_alloc((void**)&partial, (size_t)N_CHUNKS * N_GRID * sizeof(double), st));
+    GP_TRY(pool_alloc((void**)&qscale, (size_t)N_GRID * sizeof(double), st));
+    GP_TRY(pool_alloc((void**)&oscale, (size_t)N_GRID * sizeof(double), st));
+    stream_for_free = st;
     GP_CUDA(cudaMemsetAsync(yt, 0, (size_t)n_pad * m_pad, st));
     GP_CUDA(cudaMemsetAsync(Q, 0, (size_t)c_pad * m_pad, st));
     dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(m, 64));
@@ -307,7 +308,7 @@ int ThetaInt8::run(cudaStream_t st, const double* fstar, int64_t ld, double out_
 }
 
 void ThetaInt8::destroy() {
-    for (void* p : {(void*)yt, (void*)Q, (void*)partial, (void*)qscale, (void*)oscale}) if (p) cudaFree(p);
+    for (void* p : {(void*)yt, (void*)Q, (void*)partial, (void*)qscale, (void*)oscale}) pool_free(p, stream_for_free);
     yt = nullptr; Q = nullptr; partial = nullptr; qscale = oscale = nullptr;
     delete maps; maps = nullptr;
     ready = false;

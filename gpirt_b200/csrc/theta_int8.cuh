@@ -14,6 +14,7 @@ struct ThetaInt8 {
     double *partial = nullptr, *qscale = nullptr, *oscale = nullptr;
     Maps* maps = nullptr;
     bool ready = false;
+    cudaStream_t stream_for_free = nullptr;
 
     int init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n, int m);
     // logPt[k + i ldP] = out_factor * sum_j fstar[k + j ld] * y[i, j]      (k < 1001, i < n)

@@ -68,6 +68,8 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
 const char* gpirt_b200_strerror(int status);
 const char* gpirt_b200_last_error(void); /* detail of the last failure on this thread (CUDA / NCCL message) */
 int gpirt_b200_device_count(void);
+/* device memory is pooled across calls (a second gpirtMCMC() re-uses it); this hands it back to the driver */
+int gpirt_b200_release_memory(void);
 int gpirt_b200_nccl_unique_id(void* out128); /* rank 0 creates, the host distributes (any transport) */
 
 /* ---- resident sampler: state lives in HBM between calls (bench "value", step-level parity tests) ---- */
