@@ -345,7 +345,8 @@ int launch_irf_finish(cudaStream_t st, const double* irf_sum, int64_t ld, int N,
 // k_theta_prep evaluates D once per (k, j) (N m transcendentals instead of n N m) and its row sums.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_theta_prep(const double* __restrict__ fstar, double* __restrict__ D, int64_t ld,
-                                                    int N, int m, double* __restrict__ partial, int n_chunks) {
+                                                    int N, int m, double* __restrict__ partial, int n_chunks,
+                                                    const double* __restrict__ sp) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x, chunk = blockIdx.y;
     if (k >= N) return;
     const int per = (int)ceil_div(m, n_chunks), j0 = chunk * per, j1 = min(m, j0 + per);
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(128) k_theta_prep(const double* __restrict__ f
     for (int j = j0; j < j1; ++j) {
         const double v = fstar[k + (int64_t)j * ld];
         const double a = fabs(v);
-        const double d = 0.5 * a + log1p(exp(-a));
+        const double d = 0.5 * a + sp_h(sp, a);   // log(2 cosh(v/2)) = |v|/2 + log(1 + exp(-|v|))
         D[k + (int64_t)j * ld] = d;
         acc += d;
     }
@@ -369,7 +370,9 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int N, int
 int launch_theta_prep(cudaStream_t st, const double* fstar, double* D, int64_t ld, int N, int m, double* partial,
                       int n_chunks, double* rowsum) {
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)n_chunks);
-    GP_LAUNCH(k_theta_prep, grid, 128, 0, st, fstar, D, ld, N, m, partial, n_chunks);
+    const double* sp = nullptr;
+    GP_TRY(softplus_table(&sp));
+    GP_LAUNCH(k_theta_prep, grid, 128, 0, st, fstar, D, ld, N, m, partial, n_chunks, sp);
     GP_LAUNCH(k_reduce_partials, (unsigned)ceil_div(N, 128), 128, 0, st, partial, N, n_chunks, rowsum);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;

@@ -540,7 +540,7 @@ Bounce g_bounce;   // process-wide, reused across calls
 
 int host_threads_for_copy() {
     const char* e = getenv("GPIRT_COPY_THREADS");
-    int t = e ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    int t = e ? atoi(e) : (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency() * 3 / 4));
     return t < 1 ? 1 : (t > 32 ? 32 : t);
 }
 
