@@ -293,6 +293,24 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
 
+    # ------------------------------------------------------------------ chain-parallel mode (BASELINE config 4), N > 1 only
+    # every rank runs an INDEPENDENT chain of the whole workload (own seed, no communication): aggregate sweeps/s
+    if world > 1 and not args.no_extras:
+        sc = G.Sampler(data["y"], data["theta_init"], data["pm"], data["psd"], data["pstep"], seed=synthetic.SEED + 1000 + rank,
+                       device=local_rank, fstar_mode=args.fstar_mode)
+        sc.set_timing(False)
+        sc.init_draws()
+        sc.sweep(max(3, W))
+        dist.barrier()
+        ms_c = sc.sweep(K)
+        import torch
+        t = torch.tensor([ms_c], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sc.close()
+        line["chain_parallel"] = {"value": 1000.0 * K * world / float(t.item()), "unit": "sweeps/s (sum over %d independent chains)" % world,
+                                  "ms_per_step_per_chain": float(t.item()) / K, "scaling": "weak",
+                                  "note": "one full-size chain per GPU, no collective (BASELINE config 4); `value` above is the item-sharded single chain (config 3)"}
+
     # ------------------------------------------------------------------ end-to-end through the public call (host buffers)
     if not args.no_e2e:
         from gpirt_b200 import ResponseMatrix
