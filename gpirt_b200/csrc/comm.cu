@@ -11,12 +11,13 @@ typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef int (*fn_get_uid)(ncclUniqueId_t*);
 typedef int (*fn_init_rank)(void** comm, int nranks, ncclUniqueId_t id, int rank);
 typedef int (*fn_allreduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t s);
+typedef int (*fn_allgather)(const void* send, void* recv, size_t sendcount, int dtype, void* comm, cudaStream_t s);
 typedef int (*fn_destroy)(void* comm);
 typedef const char* (*fn_errstr)(int);
 
 struct Api {
     void* handle = nullptr;
-    fn_get_uid get_uid = nullptr; fn_init_rank init_rank = nullptr; fn_allreduce allreduce = nullptr;
+    fn_get_uid get_uid = nullptr; fn_init_rank init_rank = nullptr; fn_allreduce allreduce = nullptr; fn_allgather allgather = nullptr;
     fn_destroy destroy = nullptr; fn_errstr errstr = nullptr;
     bool tried = false;
 } api;
@@ -31,9 +32,10 @@ int load_api() {
             api.get_uid = (fn_get_uid)dlsym(api.handle, "ncclGetUniqueId");
             api.init_rank = (fn_init_rank)dlsym(api.handle, "ncclCommInitRank");
             api.allreduce = (fn_allreduce)dlsym(api.handle, "ncclAllReduce");
+            api.allgather = (fn_allgather)dlsym(api.handle, "ncclAllGather");
             api.destroy = (fn_destroy)dlsym(api.handle, "ncclCommDestroy");
             api.errstr = (fn_errstr)dlsym(api.handle, "ncclGetErrorString");
-            if (!api.get_uid || !api.init_rank || !api.allreduce || !api.destroy) { dlclose(api.handle); api.handle = nullptr; }
+            if (!api.get_uid || !api.init_rank || !api.allreduce || !api.allgather || !api.destroy) { dlclose(api.handle); api.handle = nullptr; }
         }
     }
     if (!api.handle) { set_last_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror()); return GPIRT_B200_ERR_NCCL; }
@@ -69,6 +71,12 @@ int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t stre
     if (c.world <= 1) return GPIRT_B200_OK;
     const int ncclFloat64 = 8, ncclSum = 0;
     return check(api.allreduce(buf, buf, count, ncclFloat64, ncclSum, c.nccl_comm, stream), "ncclAllReduce");
+}
+
+int comm_allgather_f64(Comm& c, double* buf, size_t count_per_rank, cudaStream_t stream) {
+    if (c.world <= 1) return GPIRT_B200_OK;
+    const int ncclFloat64 = 8;
+    return check(api.allgather(buf + (size_t)c.rank * count_per_rank, buf, count_per_rank, ncclFloat64, c.nccl_comm, stream), "ncclAllGather");
 }
 
 void comm_destroy(Comm& c) {

@@ -13,6 +13,8 @@ struct Comm {
 int comm_unique_id(void* out128);
 int comm_init(Comm& c, int rank, int world, const void* unique_id128);
 int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t stream);
+// in-place all-gather: rank r contributes buf[r * count_per_rank, (r+1) * count_per_rank)
+int comm_allgather_f64(Comm& c, double* buf, size_t count_per_rank, cudaStream_t stream);
 void comm_destroy(Comm& c);
 
 }  // namespace gpirt

@@ -204,12 +204,12 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(theta, (size_t)ldn)); GP_TRY(alloc(theta_star, (size_t)ldN)); GP_TRY(alloc(prior, (size_t)ldN));
     GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
     GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * CHOL_NB));
-    GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * N_GRID));
+    GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * (N_GRID + 8)));
     GP_TRY(alloc(panel_scratch, (size_t)ldn * CHOL_NB));
     lookahead.panel_scratch = panel_scratch; lookahead.ld_scratch = ldn;
     GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
-    GP_TRY(alloc(kstar, (size_t)ldn * N_GRID)); GP_TRY(alloc(s, (size_t)ldN));
+    GP_TRY(alloc(kstar, (size_t)ldn * (N_GRID + 8))); GP_TRY(alloc(s, (size_t)ldN));
     GP_TRY(alloc(logPt, (size_t)ldN * (n + 1))); GP_TRY(alloc(partial, (size_t)N_CHUNKS * N_GRID));
     GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2));
     GP_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int), stream));
@@ -305,13 +305,22 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
 // instead of two solves per item.  Depends on theta and L only, so the pipelined sweep runs it beside the ESS.
 int gpirt_b200_sampler::fstar_solves(cudaStream_t st) {
     const int N = N_GRID;
+    // with items sharded over GPUs this part would be replicated: instead every rank solves for its slice of the 1001
+    // grid columns and the slices are all-gathered (n x 1001 doubles) — the caller passes the main stream then
+    const int per = (int)ceil_div(N, comm.world), c0 = min(N, comm.rank * per), nc = min(N, c0 + per) - c0;
     Seg a = tic_on(GPIRT_B200_T_KSTAR, st);
-    GP_TRY(launch_se_cov(st, theta, n, theta_star, N, 0.0, false, kstar, ldn));              // :17
+    GP_TRY(launch_se_cov(st, theta, n, theta_star + c0, nc, 0.0, false, kstar + (int64_t)c0 * ldn, ldn));   // :17
     toc_on(a, st);
     Seg b = tic_on(GPIRT_B200_T_TRSM, st);
-    GP_TRY(gemm_f64(st, false, false, G(n, N, n, Linv, ldn, kstar, ldn, kstar2, ldn, 1.0, 0.0, TRI_A_LOWER)));   // :19
-    GP_TRY(launch_fstar_sd(st, kstar2, ldn, n, N, s));                                        // :20
-    GP_TRY(gemm_f64(st, true, false, G(n, N, n, Linv, ldn, kstar2, ldn, kstar, ldn, 1.0, 0.0, TRI_A_UPPER)));
+    if (nc > 0) {
+        GP_TRY(gemm_f64(st, false, false, G(n, nc, n, Linv, ldn, kstar + (int64_t)c0 * ldn, ldn, kstar2 + (int64_t)c0 * ldn, ldn, 1.0, 0.0, TRI_A_LOWER)));   // :19
+        GP_TRY(launch_fstar_sd(st, kstar2 + (int64_t)c0 * ldn, ldn, n, nc, s + c0));           // :20
+        GP_TRY(gemm_f64(st, true, false, G(n, nc, n, Linv, ldn, kstar2 + (int64_t)c0 * ldn, ldn, kstar + (int64_t)c0 * ldn, ldn, 1.0, 0.0, TRI_A_UPPER)));
+    }
+    if (comm.world > 1) {
+        GP_TRY(comm_allgather_f64(comm, kstar, (size_t)per * ldn, st));
+        GP_TRY(comm_allgather_f64(comm, s, (size_t)per, st));
+    }
     toc_on(b, st);
     return GPIRT_B200_OK;
 }
@@ -467,7 +476,7 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     GP_CUDA(cudaStreamWaitEvent(stream, ev_beta, 0));
     nu_ready = true;
     nu_sweep = next_sweep;
-    if (opts.fstar_mode == 0) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
+    if (opts.fstar_mode == 0 && comm.world <= 1) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
         GP_CUDA(cudaEventRecord(ev_linv, stream));
         GP_CUDA(cudaStreamWaitEvent(st_solve, ev_linv, 0));
         GP_TRY(fstar_solves(st_solve));
