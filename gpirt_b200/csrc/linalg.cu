@@ -205,9 +205,8 @@ __device__ __forceinline__ double fast_rcp(double p) {
 //   W_ij -= (a_ic / p_c) W_cj ,  W_ic = -(a_ic / p_c)  (i > c >= j;  W accumulates Lh^-1, W_cc = 1 implicit)
 // and afterwards  L = Lh D^1/2 : l_ij = a_ij / sqrt(p_j),   X = L^-1 = D^-1/2 W : x_ij = W_ij / sqrt(p_i).
 // W_ij lives transposed at S[j][i] (strict upper triangle), pivots in pv[].
-__device__ long long* g_dbg_ptr = nullptr;
-__device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o, int tid, int* status) {
-    long long* dbg = g_dbg_ptr;
+__device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o, int tid, int* status,
+                                     long long* dbg = nullptr) {
     const int j = tid & 31, i0 = tid >> 5;   // column j, rows i0 and i0 + 16
     bool bad = false;
     for (int c = 0; c < 32; ++c) {
@@ -353,8 +352,6 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A,
     double* pv = ldiag + DB;
     const int tid = threadIdx.x;
     DIAG_MARK(0);
-    if (tid == 0) g_dbg_ptr = dbg;
-    __syncthreads();
     // load the lower triangle (rows/cols >= nb padded with the identity)
     for (int idx = tid; idx < DB * DB; idx += DTHREADS) {
         const int r = idx % DB, c = idx / DB;
@@ -364,7 +361,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A,
     }
     __syncthreads();
     DIAG_MARK(1);
-    diag32_factor_invert(S, ldiag, pv, 0, tid, status);
+    diag32_factor_invert(S, ldiag, pv, 0, tid, status, dbg);
     DIAG_MARK(2);
     mm_panel<32>(S, 32, 0, tid);
     mm_syrk<32>(S, 32, 0, tid);
