@@ -191,9 +191,11 @@ int trsm_left_lower(cudaStream_t stream, bool trans, int n, int nrhs, const doub
 namespace {
 constexpr int DB = CHOL_NB, DLD = DB + 1, DTHREADS = 512;
 
-// fast 1/p for p > 0: single-precision seed + two Newton steps (4 dependent DFMAs instead of the full division routine)
+// fast 1/p for p > 0: hardware double-precision reciprocal seed (MUFU.RCP64H, ~20 bits) + two Newton steps
+// (4 dependent DFMAs instead of the full IEEE division routine; result within 1 ulp)
 __device__ __forceinline__ double fast_rcp(double p) {
-    double r = (double)__frcp_rn((float)p);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
     r = fma(r, fma(-p, r, 1.0), r);
     r = fma(r, fma(-p, r, 1.0), r);
     return r;
@@ -208,30 +210,43 @@ __device__ __forceinline__ double fast_rcp(double p) {
 __device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o, int tid, int* status,
                                      long long* dbg = nullptr) {
     const int j = tid & 31, i0 = tid >> 5;   // column j, rows i0 and i0 + 16
-    bool bad = false;
+    double* pinv_s = pv + DB;                // reciprocals of the pivots, published by the thread that produces the pivot
+    if (tid == 0) { const double p0 = S[o * DLD + o]; pv[o] = p0; pinv_s[o] = fast_rcp(p0); }
+    __syncthreads();
+    // Critical path of one step: load 1/p_c -> multiplier -> update -> (owner of a_{c+1,c+1}: reciprocal of the new
+    // pivot) -> barrier.  Everything that does not depend on 1/p_c is loaded before it.
     for (int c = 0; c < 32; ++c) {
         const int cc = o + c;
-        // (computing the next pivot one step ahead would read S[c+1][c+1] while its owner updates it: keep it simple)
-        const double p = S[cc * DLD + cc];
-        bad |= !(p > 0.0);
-        const double pinv = fast_rcp(p);
-        if (tid == 0) pv[cc] = p;
+        const bool probe = dbg && o == 0 && c == 8 && tid == 64;
+        if (probe) dbg[10] = clock64();
         // one predicated path for all lanes (no divergence): j > c updates A(i,j); j <= c updates W(i,j) stored at
         // S[j][i], where j == c is the fresh column W(i,c) = 0 - mlt * 1 (the strict upper triangle starts as zeros)
         const double other = (j == c) ? 1.0 : S[(o + j) * DLD + cc];   // a_jc, or W(c,j) which lives at S[o+j][o+c]
+        double* tgt[2];
+        double mv[2], tv[2];
+        bool active[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int i = i0 + 16 * u;
-            const double mlt = S[(o + i) * DLD + cc] * pinv;
-            double* tgt = (j > c) ? &S[(o + i) * DLD + o + j] : &S[(o + j) * DLD + o + i];
-            const bool active = (i > c) && (j <= c || i >= j);
-            if (active) *tgt = fma(-mlt, other, *tgt);
+            tgt[u] = (j > c) ? &S[(o + i) * DLD + o + j] : &S[(o + j) * DLD + o + i];
+            active[u] = (i > c) && (j <= c || i >= j);
+            mv[u] = S[(o + i) * DLD + cc];
+            tv[u] = *tgt[u];
         }
-        if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[11 + (tid ? 4 : 0)] = clock64();
+        const double pinv = pinv_s[cc];
+        if (probe) dbg[11] = clock64() + (long long)(pinv == 123.456);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!active[u]) continue;
+            const double r = fma(-(mv[u] * pinv), other, tv[u]);
+            *tgt[u] = r;
+            if (j == c + 1 && i0 + 16 * u == c + 1) { pv[cc + 1] = r; pinv_s[cc + 1] = fast_rcp(r); }   // next pivot
+        }
+        if (probe) dbg[12] = clock64();
         __syncthreads();
-        if (dbg && o == 0 && c == 8 && (tid == 0 || tid == 480)) dbg[12 + (tid ? 4 : 0)] = clock64();
+        if (probe) dbg[13] = clock64();
     }
-    if (bad && tid == 0) atomicExch(status, 1);   // not positive definite (or NaN)
+    if (tid < 32 && !(pv[o + tid] > 0.0)) atomicExch(status, 1);   // not positive definite (or NaN)
     // scale: l_ij = a_ij rsqrt(p_j) (i > j);  x_ij = W_ij rsqrt(p_i), stored at S[j][i];  diagonals
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -248,50 +263,76 @@ __device__ void diag32_factor_invert(double* S, double* ldiag, double* pv, int o
     __syncthreads();
 }
 
-// L21 = A21 X11^T, block rows ro.., block cols co.. (H x H), X11 = inverse of the diagonal block at co.
-// Thread -> row i = tid % H and the PER columns j = tid / H + t (DTHREADS / H); the PER dot products advance together
-// (one load of A21(i,k) feeds all of them; PER independent FMA chains hide the FP64 latency).
+// ---- off-diagonal block products of the recursion, on the FP64 tensor pipe straight out of shared memory ----------
+// H x H blocks as 8 x 8 DMMA fragments (m8n8k4): lane (g = lane/4, t = lane%4) supplies A(row0+g, k0+t) and
+// B(k0+t, col0+g) and owns C(row0+g, col0+2t..2t+1).  16 warps: H = 64 -> warp w does row block w%8 and the four
+// column blocks (w/8)*4.., H = 32 -> one fragment per warp.  Operands that live transposed / triangular in the shared
+// array are fetched through their index formulas, structural zeros are skipped k-step-wise (uniform per warp).
+template <int H> struct FragMap {
+    static constexpr int NF = H / 8, FPW = (NF * NF) / 16;
+    __device__ static int rb(int w) { return w % NF; }
+    __device__ static int cb(int w, int q) { return (w / NF) * FPW + q; }
+};
+
+// L21 = A21 X11^T  (block at rows ro.., cols co..; X11 = inverse of the diagonal block at co, X11(j,k) at S[co+k][co+j], k <= j)
 template <int H>
 __device__ void mm_panel(double* S, int ro, int co, int tid) {
-    constexpr int PER = (H * H) / DTHREADS, JS = DTHREADS / H;
-    const int i = tid % H, jb = tid / H;
-    const double* a = S + (ro + i) * DLD + co;
-    double acc[PER];
+    using FM = FragMap<H>;
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = FM::rb(w) * 8;
+    double acc[FM::FPW][2];
 #pragma unroll
-    for (int t = 0; t < PER; ++t) acc[t] = 0.0;
-    for (int k = 0; k < H; ++k) {                       // X11(j,k) = S[(co+k)][co+j], k <= j
-        const double av = a[k];
-        const double* xr = S + (co + k) * DLD + co;
+    for (int q = 0; q < FM::FPW; ++q) acc[q][0] = acc[q][1] = 0.0;
+    const int cmax = FM::cb(w, FM::FPW - 1) * 8 + 7;          // largest column of this warp: k runs to it
+    for (int k0 = 0; k0 <= cmax; k0 += 4) {
+        const double av = S[(ro + r0 + g) * DLD + co + k0 + t];
 #pragma unroll
-        for (int t = 0; t < PER; ++t) {
-            const int j = jb + t * JS;
-            if (k <= j) acc[t] = fma(av, xr[j], acc[t]);
+        for (int q = 0; q < FM::FPW; ++q) {
+            const int c0 = FM::cb(w, q) * 8;
+            if (k0 > c0 + 7) continue;                          // X11(j,k) = 0 for k > j
+            const int j = c0 + g, k = k0 + t;
+            const double bv = (k <= j) ? S[(co + k) * DLD + co + j] : 0.0;
+            dmma_8x8x4(acc[q][0], acc[q][1], av, bv);
         }
     }
-    __syncthreads();
+    __syncthreads();                                            // everyone has read A21 before it is overwritten
 #pragma unroll
-    for (int t = 0; t < PER; ++t) S[(ro + i) * DLD + co + jb + t * JS] = acc[t];
+    for (int q = 0; q < FM::FPW; ++q) {
+        const int c0 = FM::cb(w, q) * 8;
+        S[(ro + r0 + g) * DLD + co + c0 + 2 * t] = acc[q][0];
+        S[(ro + r0 + g) * DLD + co + c0 + 2 * t + 1] = acc[q][1];
+    }
     __syncthreads();
 }
 
 // A22 -= L21 L21^T (lower triangle incl. diagonal); A22 at (ro, ro), L21 at (ro, co)
 template <int H>
 __device__ void mm_syrk(double* S, int ro, int co, int tid) {
-    constexpr int PER = (H * H) / DTHREADS, JS = DTHREADS / H;
-    const int i = tid % H, jb = tid / H;
-    const double* a = S + (ro + i) * DLD + co;
-    double acc[PER];
+    using FM = FragMap<H>;
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int rbk = FM::rb(w), r0 = rbk * 8;
+    double acc[FM::FPW][2];
 #pragma unroll
-    for (int t = 0; t < PER; ++t) acc[t] = 0.0;
-    for (int k = 0; k < H; ++k) {
-        const double av = a[k];
+    for (int q = 0; q < FM::FPW; ++q) acc[q][0] = acc[q][1] = 0.0;
+    if (FM::cb(w, 0) <= rbk) {                                  // at least one fragment on or below the diagonal
+        for (int k0 = 0; k0 < H; k0 += 4) {
+            const double av = S[(ro + r0 + g) * DLD + co + k0 + t];
 #pragma unroll
-        for (int t = 0; t < PER; ++t) acc[t] = fma(av, S[(ro + jb + t * JS) * DLD + co + k], acc[t]);
-    }
+            for (int q = 0; q < FM::FPW; ++q) {
+                const int cbk = FM::cb(w, q);
+                if (cbk > rbk) continue;
+                const double bv = S[(ro + cbk * 8 + g) * DLD + co + k0 + t];   // L21(j, k)
+                dmma_8x8x4(acc[q][0], acc[q][1], av, bv);
+            }
+        }
 #pragma unroll
-    for (int t = 0; t < PER; ++t) {
-        const int j = jb + t * JS;
-        if (i >= j) S[(ro + i) * DLD + ro + j] -= acc[t];
+        for (int q = 0; q < FM::FPW; ++q) {
+            const int cbk = FM::cb(w, q);
+            if (cbk > rbk) continue;
+            const int i = r0 + g, j = cbk * 8 + 2 * t;
+            if (i >= j) S[(ro + i) * DLD + ro + j] -= acc[q][0];
+            if (i >= j + 1) S[(ro + i) * DLD + ro + j + 1] -= acc[q][1];
+        }
     }
     __syncthreads();
 }
@@ -299,37 +340,52 @@ __device__ void mm_syrk(double* S, int ro, int co, int tid) {
 // X21 = -X22 (L21 X11); X21(i,j) is stored at S[co+j][ro+i]
 template <int H>
 __device__ void mm_inv_offdiag(double* S, int ro, int co, int tid) {
-    constexpr int PER = (H * H) / DTHREADS, JS = DTHREADS / H;
-    const int i = tid % H, jb = tid / H;
-    double acc[PER];
+    using FM = FragMap<H>;
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = FM::rb(w) * 8;
+    double acc[FM::FPW][2];
     // T = L21 X11 into the X21 slot:  T(i,j) = sum_{k >= j} L21(i,k) X11(k,j),  X11(k,j) = S[co+j][co+k]
-    {
-        const double* a = S + (ro + i) * DLD + co;
 #pragma unroll
-        for (int t = 0; t < PER; ++t) acc[t] = 0.0;
-        for (int k = 0; k < H; ++k) {
-            const double av = a[k];
+    for (int q = 0; q < FM::FPW; ++q) acc[q][0] = acc[q][1] = 0.0;
+    const int cmin = FM::cb(w, 0) * 8;                          // smallest column of this warp: k starts at its fragment
+    for (int k0 = (cmin / 4) * 4; k0 < H; k0 += 4) {
+        const double av = S[(ro + r0 + g) * DLD + co + k0 + t];
 #pragma unroll
-            for (int t = 0; t < PER; ++t) {
-                const int j = jb + t * JS;
-                if (k >= j) acc[t] = fma(av, S[(co + j) * DLD + co + k], acc[t]);
-            }
+        for (int q = 0; q < FM::FPW; ++q) {
+            const int c0 = FM::cb(w, q) * 8;
+            if (k0 + 3 < c0) continue;                          // X11(k,j) = 0 for k < j
+            const int j = c0 + g, k = k0 + t;
+            const double bv = (k >= j) ? S[(co + j) * DLD + co + k] : 0.0;
+            dmma_8x8x4(acc[q][0], acc[q][1], av, bv);
         }
+    }
 #pragma unroll
-        for (int t = 0; t < PER; ++t) S[(co + jb + t * JS) * DLD + ro + i] = acc[t];
+    for (int q = 0; q < FM::FPW; ++q) {
+        const int c0 = FM::cb(w, q) * 8;
+        S[(co + c0 + 2 * t) * DLD + ro + r0 + g] = acc[q][0];
+        S[(co + c0 + 2 * t + 1) * DLD + ro + r0 + g] = acc[q][1];
     }
     __syncthreads();
     // X21(i,j) = - sum_{k <= i} X22(i,k) T(k,j),  X22(i,k) = S[ro+k][ro+i],  T(k,j) = S[co+j][ro+k]
 #pragma unroll
-    for (int t = 0; t < PER; ++t) acc[t] = 0.0;
-    for (int k = 0; k <= i; ++k) {
-        const double xv = S[(ro + k) * DLD + ro + i];
+    for (int q = 0; q < FM::FPW; ++q) acc[q][0] = acc[q][1] = 0.0;
+    for (int k0 = 0; k0 <= r0 + 7; k0 += 4) {                   // X22(i,k) = 0 for k > i
+        const int i = r0 + g, k = k0 + t;
+        const double av = (k <= i) ? S[(ro + k) * DLD + ro + i] : 0.0;
 #pragma unroll
-        for (int t = 0; t < PER; ++t) acc[t] = fma(xv, S[(co + jb + t * JS) * DLD + ro + k], acc[t]);
+        for (int q = 0; q < FM::FPW; ++q) {
+            const int c0 = FM::cb(w, q) * 8;
+            const double bv = S[(co + c0 + g) * DLD + ro + k];
+            dmma_8x8x4(acc[q][0], acc[q][1], av, bv);
+        }
     }
-    __syncthreads();
+    __syncthreads();                                            // T fully consumed before X21 replaces it
 #pragma unroll
-    for (int t = 0; t < PER; ++t) S[(co + jb + t * JS) * DLD + ro + i] = -acc[t];
+    for (int q = 0; q < FM::FPW; ++q) {
+        const int c0 = FM::cb(w, q) * 8;
+        S[(co + c0 + 2 * t) * DLD + ro + r0 + g] = -acc[q][0];
+        S[(co + c0 + 2 * t + 1) * DLD + ro + r0 + g] = -acc[q][1];
+    }
     __syncthreads();
 }
 
@@ -397,7 +453,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A,
 int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv, int64_t ldd, int* d_status,
                    CholLookahead* la) {
     if (n <= 0) return GPIRT_B200_OK;
-    constexpr size_t smem = (size_t)(DB * DLD + 2 * DB) * sizeof(double);
+    constexpr size_t smem = (size_t)(DB * DLD + 3 * DB) * sizeof(double);
     static bool configured = false;
     if (!configured) {
         GP_CUDA(cudaFuncSetAttribute(k_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -429,8 +485,7 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
             cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "k_diag128 phases (cycles): load %lld | diag32 %lld | panel+syrk32 %lld | diag32+inv32 %lld | panel64 %lld | syrk64 %lld | f_i_64 %lld | inv64 %lld | store %lld | total %lld\n",
                     h[1]-h[0], h[2]-h[1], h[3]-h[2], h[4]-h[3], h[5]-h[4], h[6]-h[5], h[7]-h[6], h[8]-h[7], h[9]-h[8], h[9]-h[0]);
-            fprintf(stderr, "step c=8: warp0 work %lld barrier %lld | warp15 work %lld barrier %lld | skew start %lld\n",
-                    h[11]-h[10], h[12]-h[11], h[15]-h[14], h[16]-h[15], h[14]-h[10]);
+            fprintf(stderr, "step c=8 (warp 2): pivot+rcp %lld | update %lld | barrier %lld\n", h[11]-h[10], h[12]-h[11], h[13]-h[12]);
         }
         const int rem = n - k0 - nb;
         if (rem <= 0) {
