@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--ess-samples", type=int, default=300)
     ap.add_argument("--fstar-mode", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -339,6 +340,28 @@ def main():
                        "note": "gpirtMCMC(sample_iterations=%d, burn_iterations=0) wall time incl. setup, initial draws, H2D of y "
                                "and D2H of every theta/beta/f draw (reference output contract)" % Ke}
         del out
+
+    # ------------------------------------------------------------------ theta ESS/sec (second half of BASELINE's metric), N = 1 only
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            from gpirt_b200 import ResponseMatrix
+            from gpirt_b200.diagnostics import ess_geyer
+            S_ess, B_ess = args.ess_samples, 50
+            t0 = time.perf_counter()
+            ch = G.gpirtMCMC(ResponseMatrix(y_loc), S_ess, B_ess, beta_prior_means=data["pm"], beta_prior_sds=data["psd"],
+                             beta_proposal_sds=data["pstep"], theta_init=data["theta_init"], seed=synthetic.SEED, device=local_rank,
+                             store_f=False, fstar_mode=args.fstar_mode)
+            el_ess = time.perf_counter() - t0
+            ess = ess_geyer(ch["theta"][1:])
+            ess = ess[np.isfinite(ess)]
+            line["theta_ess"] = {"samples": S_ess, "burn": B_ess, "seconds": el_ess, "ess_median": float(np.median(ess)),
+                                 "ess_min": float(ess.min()), "ess_per_sec_median": float(np.median(ess) / el_ess),
+                                 "ess_per_sec_min": float(ess.min() / el_ess),
+                                 "estimator": "Geyer initial positive sequence per respondent; seconds = wall time of the "
+                                              "gpirtMCMC(S, B, store_f=False) call incl. burn-in",
+                                 "corr_with_generating_theta": float(abs(np.corrcoef(ch["theta"][1:].mean(axis=0), data["theta_true"])[0, 1]))}
+        except Exception as ex:
+            line["theta_ess"] = {"error": repr(ex)}
 
     # ------------------------------------------------------------------ the other single-GPU configs, briefly (N = 1 only)
     if rank == 0 and world == 1 and args.workload == "c3" and not args.no_extras:
