@@ -321,8 +321,8 @@ def main():
                       beta_proposal_sds=data["pstep"][:, j0:j1], theta_init=data["theta_init"], seed=synthetic.SEED,
                       device=local_rank, fstar_mode=args.fstar_mode)
         shard = (rank, world, m, j0, fresh_uid()) if world > 1 else None
-        G.gpirtMCMC(yrm, 1, 0, shard=shard, **common)     # warm the call path (allocator, pinning)
-        shard = (rank, world, m, j0, fresh_uid()) if world > 1 else None
+        G.gpirtMCMC(yrm, 1, 0, shard=shard, **common)     # warm the call path (allocator, pinning, communicator)
+        shard = (rank, world, m, j0, None) if world > 1 else None   # re-use the communicator of the previous call
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()

@@ -51,8 +51,12 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError("gpirt_b200: %s is missing — build it with `python -m gpirt_b200.build` "
-                          "(there is no CPU fallback)" % LIB_PATH)
+        try:   # a source-only checkout: compile the CUDA library now (nvcc cross-compiles, no GPU needed)
+            from .build import build
+            build()
+        except Exception as ex:
+            raise ImportError("gpirt_b200: %s is missing and could not be built (%s) — run `python -m gpirt_b200.build` "
+                              "(there is no CPU fallback)" % (LIB_PATH, ex))
     L = C.CDLL(LIB_PATH)
     L.gpirt_b200_strerror.restype = C.c_char_p
     L.gpirt_b200_last_error.restype = C.c_char_p

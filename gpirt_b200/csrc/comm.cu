@@ -57,14 +57,26 @@ int comm_unique_id(void* out128) {
     return GPIRT_B200_OK;
 }
 
+// The communicator outlives the sampler: ncclCommInitRank costs 0.3-3 s, far more than a short MCMC call.  A call that
+// passes a unique id creates (and caches) a communicator; a call with world_size > 1 and NO id re-uses the cached one
+// (same rank / world).  All ranks must take the same decision, as with any collective set-up.
+static struct { void* comm = nullptr; int rank = -1, world = 0; } g_cached;
+
 int comm_init(Comm& c, int rank, int world, const void* unique_id128) {
     c.rank = rank; c.world = world;
     if (world <= 1) return GPIRT_B200_OK;
-    if (!unique_id128) { set_last_error("world_size > 1 needs opts.nccl_unique_id"); return GPIRT_B200_ERR_ARG; }
     GP_TRY(load_api());
+    if (!unique_id128) {
+        if (g_cached.comm && g_cached.rank == rank && g_cached.world == world) { c.nccl_comm = g_cached.comm; return GPIRT_B200_OK; }
+        set_last_error("world_size > 1 needs opts.nccl_unique_id (no cached communicator for rank %d of %d)", rank, world);
+        return GPIRT_B200_ERR_ARG;
+    }
+    if (g_cached.comm) { api.destroy(g_cached.comm); g_cached.comm = nullptr; }
     ncclUniqueId_t id;
     std::memcpy(&id, unique_id128, sizeof(id));
-    return check(api.init_rank(&c.nccl_comm, world, id, rank), "ncclCommInitRank");
+    GP_TRY(check(api.init_rank(&c.nccl_comm, world, id, rank), "ncclCommInitRank"));
+    g_cached.comm = c.nccl_comm; g_cached.rank = rank; g_cached.world = world;
+    return GPIRT_B200_OK;
 }
 
 int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t stream) {
@@ -79,9 +91,11 @@ int comm_allgather_f64(Comm& c, double* buf, size_t count_per_rank, cudaStream_t
     return check(api.allgather(buf + (size_t)c.rank * count_per_rank, buf, count_per_rank, ncclFloat64, c.nccl_comm, stream), "ncclAllGather");
 }
 
-void comm_destroy(Comm& c) {
-    if (c.nccl_comm && api.destroy) api.destroy(c.nccl_comm);
-    c.nccl_comm = nullptr;
+void comm_destroy(Comm& c) { c.nccl_comm = nullptr; }   // the cached communicator stays alive for the next call
+
+void comm_shutdown() {
+    if (g_cached.comm && api.destroy) api.destroy(g_cached.comm);
+    g_cached.comm = nullptr; g_cached.rank = -1; g_cached.world = 0;
 }
 
 }  // namespace gpirt

@@ -550,6 +550,9 @@ Bounce g_bounce;   // process-wide, reused across calls
 int host_threads_for_copy() {
     const char* e = getenv("GPIRT_COPY_THREADS");
     int t = e ? atoi(e) : (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency() * 3 / 4));
+    const char* ws = getenv("WORLD_SIZE");   // one process per GPU on the same host: share the cores
+    const int world = ws ? atoi(ws) : 1;
+    if (!e && world > 1) t = std::max(2, t / world);
     return t < 1 ? 1 : (t > 32 ? 32 : t);
 }
 
@@ -616,6 +619,7 @@ const char* gpirt_b200_strerror(int status) {
 const char* gpirt_b200_last_error(void) { return gpirt::last_error(); }
 
 int gpirt_b200_release_memory(void) {
+    comm_shutdown();
     int dev = 0;
     GP_CUDA(cudaGetDevice(&dev));
     cudaMemPool_t pool;

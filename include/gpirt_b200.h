@@ -44,7 +44,8 @@ typedef struct gpirt_b200_opts {
     int32_t rank, world_size;
     int64_t m_global;     /* total items over all ranks */
     int64_t item_offset;  /* global index of this rank's first item (y, priors and outputs are the LOCAL block) */
-    const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (rank 0: gpirt_b200_nccl_unique_id) */
+    const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (rank 0: gpirt_b200_nccl_unique_id);
+                                   NULL on a later call re-uses the communicator the previous call created */
 } gpirt_b200_opts;
 
 /* Progress / interrupt callback: called once per iteration with percent complete (as the reference's Rprintf,
@@ -68,7 +69,7 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
 const char* gpirt_b200_strerror(int status);
 const char* gpirt_b200_last_error(void); /* detail of the last failure on this thread (CUDA / NCCL message) */
 int gpirt_b200_device_count(void);
-/* device memory is pooled across calls (a second gpirtMCMC() re-uses it); this hands it back to the driver */
+/* device memory and the NCCL communicator are kept across calls (a second gpirtMCMC() re-uses them); this releases them */
 int gpirt_b200_release_memory(void);
 int gpirt_b200_nccl_unique_id(void* out128); /* rank 0 creates, the host distributes (any transport) */
 
