@@ -95,16 +95,14 @@ int gpirt_b200_chol_lower(double* S, int64_t n) {
     GP_TRY(have_device());
     if (n == 0) return GPIRT_B200_OK;
     const int64_t ld = round_up(n, 8);
-    DevBuf a, dinv;
-    int* st = nullptr;
-    GP_TRY(a.alloc(ld * n)); GP_TRY(dinv.alloc(ld * CHOL_NB));
-    GP_CUDA(cudaMalloc((void**)&st, sizeof(int)));
-    GP_CUDA(cudaMemset(st, 0, sizeof(int)));
+    DevBuf a, dinv, flag;   // flag: one double-sized slot used as the int status word
+    GP_TRY(a.alloc(ld * n)); GP_TRY(dinv.alloc(ld * CHOL_NB)); GP_TRY(flag.alloc(1));
+    int* st = reinterpret_cast<int*>(flag.p);
+    GP_CUDA(cudaMemset(st, 0, sizeof(double)));
     GP_TRY(h2d(a.p, ld, S, n, n, n));
     int rc = potrf_lower_rl(0, a.p, ld, (int)n, dinv.p, ld, st);
     int h = 0;
     if (rc == GPIRT_B200_OK && cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GPIRT_B200_ERR_CUDA;
-    cudaFree(st);
     if (rc) return rc;
     if (h) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
     GP_TRY(d2h(S, n, a.p, ld, n, n));

@@ -122,13 +122,14 @@ struct gpirt_b200_sampler {
         cudaEventRecord(cur.b, stream);
         pending.push_back(cur);
     }
-    void flush_timers() {  // call after the stream has been synchronised
+    void flush_timers() {  // call after ALL of the sampler's streams have been synchronised
         for (auto& sg : pending) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, sg.a, sg.b) == cudaSuccess) { ms[sg.timer] += t; calls[sg.timer] += 1; }
             pool.push_back(sg.a); pool.push_back(sg.b);
         }
         pending.clear();
+        cudaGetLastError();   // a not-ready event must not surface later as a launch failure
     }
 
     RngKey key_at(uint32_t sweep) const { RngKey k = key; k.sweep = sweep; return k; }
@@ -256,6 +257,8 @@ int gpirt_b200_sampler::check_status() {
     int h[4];
     GP_CUDA(cudaMemcpyAsync(h, status, sizeof(h), cudaMemcpyDeviceToHost, stream));
     GP_CUDA(cudaStreamSynchronize(stream));
+    if (st_lz) GP_CUDA(cudaStreamSynchronize(st_lz));       // side streams may still run the next sweep's K* solves
+    if (st_beta) GP_CUDA(cudaStreamSynchronize(st_beta));
     flush_timers();
     if (h[0]) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
     if (h[1]) { set_last_error("elliptical slice sampler did not terminate (NaN log-likelihood?)"); return GPIRT_B200_ERR_ESS; }
