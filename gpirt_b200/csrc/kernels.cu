@@ -70,7 +70,7 @@ __global__ void k_ingest_y(const double* __restrict__ y, int n, int m, int8_t* _
     else if (isnan(v)) atomicAdd(n_missing, 1ull);
     else atomicAdd(n_bad, 1ull);
     y8[i + (int64_t)j * ldy8] = c;
-    yd[i + (int64_t)j * ldyd] = (double)c;
+    if (yd) yd[i + (int64_t)j * ldyd] = (double)c;
 }
 int launch_ingest_y(cudaStream_t st, const double* y, int n, int m, int8_t* y8, int64_t ldy8, double* yd, int64_t ldyd,
                     unsigned long long* n_missing, unsigned long long* n_bad) {

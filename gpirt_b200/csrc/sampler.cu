@@ -201,7 +201,13 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     }
 
     const size_t nm = (size_t)ldn * m, Nm = (size_t)ldN * m;
-    GP_TRY(alloc(y8, (size_t)ldy8 * m)); GP_TRY(alloc(yd, nm));
+    {   // the theta contraction runs on the int8 tensor cores (y is an exact int8 operand); GPIRT_THETA_INT8=0 keeps
+        // the FP64 DMMA contraction instead, which needs y as doubles
+        const char* e = getenv("GPIRT_THETA_INT8");
+        use_ti8 = e ? atoi(e) != 0 : true;
+    }
+    GP_TRY(alloc(y8, (size_t)ldy8 * m));
+    if (!use_ti8) GP_TRY(alloc(yd, nm));
     GP_TRY(alloc(theta, (size_t)ldn)); GP_TRY(alloc(theta_star, (size_t)ldN)); GP_TRY(alloc(prior, (size_t)ldN));
     GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
     GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * CHOL_NB));
@@ -217,7 +223,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream));
     GP_CUDA(cudaMemsetAsync(irf_sum, 0, Nm * sizeof(double), stream));
     GP_CUDA(cudaMemsetAsync(y8, 0, (size_t)ldy8 * m, stream));
-    GP_CUDA(cudaMemsetAsync(yd, 0, nm * sizeof(double), stream));
+    if (yd) GP_CUDA(cudaMemsetAsync(yd, 0, nm * sizeof(double), stream));
     GP_CUDA(cudaMemsetAsync(f, 0, nm * sizeof(double), stream));
     GP_CUDA(cudaMemsetAsync(fstar, 0, Nm * sizeof(double), stream));
     GP_CUDA(cudaMemsetAsync(logPt, 0, (size_t)ldN * (n + 1) * sizeof(double), stream));
@@ -240,14 +246,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         return GPIRT_B200_ERR_Y_VALUE;
     }
     has_missing = cnt[0] != 0;
-    {   // the theta contraction runs on the int8 tensor cores when y has no missing cells (|y| = 1 everywhere)
-        const char* e = getenv("GPIRT_THETA_INT8");
-        const bool want = e ? atoi(e) != 0 : true;
-        if (want && !has_missing) {
-            GP_TRY(ti8.init(stream, y8, ldy8, n, m));
-            use_ti8 = true;
-        }
-    }
+    if (use_ti8) GP_TRY(ti8.init(stream, y8, ldy8, n, m, has_missing));
     GP_TRY(step_rebuild());                                                         // gpirtMCMC.cpp:15-17
     GP_CUDA(cudaStreamSynchronize(stream));
     return check_status();
@@ -377,11 +376,12 @@ int gpirt_b200_sampler::step_draw_theta(uint32_t sweep) {
     toc();
     tic(GPIRT_B200_T_THETA_GEMM);
     // logP^T[k,i] = 1/2 sum_j f*_kj y_ij   (y = 0 where missing)
-    if (use_ti8) GP_TRY(ti8.run(stream, fstar, ldN, 0.5, logPt, ldN));
+    if (use_ti8) GP_TRY(ti8.run(stream, fstar, ldN, 0.5, logPt, ldN, false, false));
     else GP_TRY(gemm_f64(stream, false, true, G(N, n, m, fstar, ldN, yd, ldn, logPt, ldN, 0.5, 0.0, TRI_NONE)));
     const double* rs_for_draw = rowsum;
     if (has_missing) {  // - sum_j obs_ij D_kj with obs = |y|
-        GP_TRY(gemm_f64(stream, false, true, G(N, n, m, Dmat, ldN, yd, ldn, logPt, ldN, -1.0, 1.0, TRI_NONE, 1)));
+        if (use_ti8) GP_TRY(ti8.run(stream, Dmat, ldN, -1.0, logPt, ldN, true, true));
+        else GP_TRY(gemm_f64(stream, false, true, G(N, n, m, Dmat, ldN, yd, ldn, logPt, ldN, -1.0, 1.0, TRI_NONE, 1)));
         rs_for_draw = nullptr;
     }
     toc();

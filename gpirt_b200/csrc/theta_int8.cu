@@ -77,7 +77,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __global__ void __launch_bounds__(256, 1)
 k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int num_kblocks,
               int mtiles, int n_rows, int n_grid, const double* __restrict__ scale, double* __restrict__ logPt,
-              int64_t ldP) {
+              int64_t ldP, int accumulate) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
     uint64_t* bars = (uint64_t*)(smem + TI_STAGES * TI_STAGE_BYTES);
@@ -149,7 +149,10 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 double v = (double)(int)r[8 * h + 7];
 #pragma unroll
                 for (int s = 6; s >= 0; --s) v = fma(v, 0.0078125, (double)(int)r[8 * h + s]);
-                if (i < n_rows && k < n_grid) logPt[(int64_t)k + (int64_t)i * ldP] = scale[k] * v;
+                if (i < n_rows && k < n_grid) {
+                    double* dst = logPt + (int64_t)k + (int64_t)i * ldP;
+                    *dst = accumulate ? fma(scale[k], v, *dst) : scale[k] * v;
+                }
             }
         }
     }
@@ -163,12 +166,13 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // ---- operand preparation ----------------------------------------------------------------------------------------------
 // Yt[i][j] (int8, row stride m_pad) from y8[i + j ldy] : 64 x 64 byte tiles through shared memory
 __global__ void __launch_bounds__(256) k_build_yt(const int8_t* __restrict__ y8, int64_t ldy, int n, int m,
-                                                  int8_t* __restrict__ yt, int64_t m_pad) {
+                                                  int8_t* __restrict__ yt, int64_t m_pad, int take_abs) {
     __shared__ int8_t tile[64][65];
     const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
     for (int e = threadIdx.x; e < 64 * 64; e += 256) {
         const int ii = e % 64, jj = e / 64;
-        tile[jj][ii] = (i0 + ii < n && j0 + jj < m) ? y8[(i0 + ii) + (int64_t)(j0 + jj) * ldy] : (int8_t)0;
+        int8_t v = (i0 + ii < n && j0 + jj < m) ? y8[(i0 + ii) + (int64_t)(j0 + jj) * ldy] : (int8_t)0;
+        tile[jj][ii] = (take_abs && v < 0) ? (int8_t)(-v) : v;
     }
     __syncthreads();
     for (int e = threadIdx.x; e < 64 * 64; e += 256) {
@@ -262,9 +266,9 @@ int make_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t row_bytes, ui
 
 }  // namespace
 
-struct ThetaInt8::Maps { CUtensorMap a, b; };
+struct ThetaInt8::Maps { CUtensorMap a, a_abs, b; };
 
-int ThetaInt8::init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n_, int m_) {
+int ThetaInt8::init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n_, int m_, bool with_observed_mask) {
     n = n_; m = m_;
     m_pad = round_up(m, TI_BK);
     n_pad = round_up(n, TI_BM);
@@ -278,19 +282,28 @@ int ThetaInt8::init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n_, int 
     GP_CUDA(cudaMemsetAsync(yt, 0, (size_t)n_pad * m_pad, st));
     GP_CUDA(cudaMemsetAsync(Q, 0, (size_t)c_pad * m_pad, st));
     dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(m, 64));
-    GP_LAUNCH(k_build_yt, grid, 256, 0, st, y8, ldy, n, m, yt, m_pad);
+    GP_LAUNCH(k_build_yt, grid, 256, 0, st, y8, ldy, n, m, yt, m_pad, 0);
     GP_CUDA(cudaGetLastError());
     maps = new Maps();
     GP_TRY(make_map(&maps->a, yt, (uint64_t)n_pad, (uint64_t)m_pad, TI_BM));
+    if (with_observed_mask) {   // |y| in {0,1}: the observed-cell operand of the second product (missing data)
+        GP_TRY(pool_alloc((void**)&yt_abs, (size_t)n_pad * m_pad, st));
+        GP_CUDA(cudaMemsetAsync(yt_abs, 0, (size_t)n_pad * m_pad, st));
+        GP_LAUNCH(k_build_yt, grid, 256, 0, st, y8, ldy, n, m, yt_abs, m_pad, 1);
+        GP_CUDA(cudaGetLastError());
+        GP_TRY(make_map(&maps->a_abs, yt_abs, (uint64_t)n_pad, (uint64_t)m_pad, TI_BM));
+    }
     GP_TRY(make_map(&maps->b, Q, (uint64_t)c_pad, (uint64_t)m_pad, TI_BN));
     GP_CUDA(cudaFuncSetAttribute(k_igemm_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM));
     ready = true;
     return GPIRT_B200_OK;
 }
 
-// logPt[k + i ldP] = out_factor * sum_j fstar[k,j] y[i,j]
-int ThetaInt8::run(cudaStream_t st, const double* fstar, int64_t ld, double out_factor, double* logPt, int64_t ldP) {
+// logPt[k + i ldP] (+)= out_factor * sum_j src[k,j] y[i,j]     (observed_mask: |y| instead of y)
+int ThetaInt8::run(cudaStream_t st, const double* fstar, int64_t ld, double out_factor, double* logPt, int64_t ldP,
+                   bool observed_mask, bool accumulate) {
     if (!ready) { set_last_error("ThetaInt8 not initialised"); return GPIRT_B200_ERR_ARG; }
+    if (observed_mask && !yt_abs) { set_last_error("ThetaInt8: observed-mask operand was not built"); return GPIRT_B200_ERR_ARG; }
     {
         dim3 grid((unsigned)ceil_div(N_GRID, 128), (unsigned)N_CHUNKS);
         GP_LAUNCH(k_rowabsmax_partial, grid, 128, 0, st, fstar, ld, N_GRID, m, partial, N_CHUNKS);
@@ -301,15 +314,15 @@ int ThetaInt8::run(cudaStream_t st, const double* fstar, int64_t ld, double out_
         GP_LAUNCH(k_slice_digits, grid, 256, 0, st, fstar, ld, N_GRID, m, qscale, Q, m_pad);
     }
     const int mtiles = (int)(n_pad / TI_BM), ntiles = (int)(c_pad / TI_BN);
-    GP_LAUNCH(k_igemm_theta, (unsigned)(mtiles * ntiles), 256, TI_SMEM, st, maps->a, maps->b, (int)(m_pad / TI_BK), mtiles, n,
-              N_GRID, oscale, logPt, ldP);
+    GP_LAUNCH(k_igemm_theta, (unsigned)(mtiles * ntiles), 256, TI_SMEM, st, observed_mask ? maps->a_abs : maps->a, maps->b,
+              (int)(m_pad / TI_BK), mtiles, n, N_GRID, oscale, logPt, ldP, accumulate ? 1 : 0);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
 }
 
 void ThetaInt8::destroy() {
-    for (void* p : {(void*)yt, (void*)Q, (void*)partial, (void*)qscale, (void*)oscale}) pool_free(p, stream_for_free);
-    yt = nullptr; Q = nullptr; partial = nullptr; qscale = oscale = nullptr;
+    for (void* p : {(void*)yt, (void*)yt_abs, (void*)Q, (void*)partial, (void*)qscale, (void*)oscale}) pool_free(p, stream_for_free);
+    yt = nullptr; yt_abs = nullptr; Q = nullptr; partial = nullptr; qscale = oscale = nullptr;
     delete maps; maps = nullptr;
     ready = false;
 }

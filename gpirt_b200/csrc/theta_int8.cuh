@@ -10,15 +10,17 @@ struct ThetaInt8 {
     int n = 0, m = 0;
     int64_t m_pad = 0, n_pad = 0, c_pad = 0;
     int8_t* yt = nullptr;        // n_pad x m_pad, K-major: responses {+1,-1,0}
+    int8_t* yt_abs = nullptr;    // |y| in {0,1} (only when there are missing cells)
     int8_t* Q = nullptr;         // c_pad x m_pad, K-major: digit s of grid row k at row 8 k + s
     double *partial = nullptr, *qscale = nullptr, *oscale = nullptr;
     Maps* maps = nullptr;
     bool ready = false;
     cudaStream_t stream_for_free = nullptr;
 
-    int init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n, int m);
-    // logPt[k + i ldP] = out_factor * sum_j fstar[k + j ld] * y[i, j]      (k < 1001, i < n)
-    int run(cudaStream_t st, const double* fstar, int64_t ld, double out_factor, double* logPt, int64_t ldP);
+    int init(cudaStream_t st, const int8_t* y8, int64_t ldy, int n, int m, bool with_observed_mask);
+    // logPt[k + i ldP] (+)= out_factor * sum_j src[k + j ld] * y[i, j]     (k < 1001, i < n; observed_mask: |y|)
+    int run(cudaStream_t st, const double* src, int64_t ld, double out_factor, double* logPt, int64_t ldP,
+            bool observed_mask, bool accumulate);
     void destroy();
 };
 

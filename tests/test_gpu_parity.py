@@ -220,11 +220,13 @@ def test_step_draw_theta(G, O, n, m, missing):
     s.close()
 
 
-@pytest.mark.parametrize("n,m", [(130, 129), (1100, 700), (4096, 300)])
-def test_theta_int8_tensor_core_path_matches_fp64_path(G, O, n, m, monkeypatch):
-    """tcgen05 int8 (exact integer) contraction vs the FP64 DMMA contraction vs the oracle, no missing data"""
+@pytest.mark.parametrize("n,m,missing", [(130, 129, 0.0), (1100, 700, 0.0), (4096, 300, 0.0),
+                                         (130, 129, 0.1), (1100, 700, 0.03), (257, 1000, 0.3)])
+def test_theta_int8_tensor_core_path_matches_fp64_path(G, O, n, m, missing, monkeypatch):
+    """tcgen05 int8 (exact integer) contraction vs the FP64 DMMA contraction vs the oracle; with missing cells the
+    int8 path adds a second product of the observed mask |y| with the digit planes of D = log 2cosh(f*/2)"""
     from gpirt_b200 import _lib
-    prob = make_problem(n, m, seed=n + m, missing=0.0, grid_theta=True)
+    prob = make_problem(n, m, seed=n + m, missing=missing, grid_theta=True)
     rs = np.random.RandomState(7)
     fstar = np.asfortranarray(rs.randn(1001, m).cumsum(axis=0) * 0.04 + 3.0 * rs.randn(1, m))
     fstar[17, 3] = 0.0; fstar[500, :] *= 1e-6; fstar[900, 0] = 37.5        # zeros, tiny row, large entry
