@@ -17,7 +17,7 @@ EXPORTS = [
     "gpirt_b200_sampler_sweep", "gpirt_b200_sampler_step", "gpirt_b200_sampler_get", "gpirt_b200_sampler_set",
     "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_set_pipeline",
     "gpirt_b200_sampler_launches",
-    "gpirt_b200_sampler_destroy", "gpirt_b200_se_cov", "gpirt_b200_chol_lower", "gpirt_b200_dgemm",
+    "gpirt_b200_sampler_destroy", "gpirt_b200_se_cov", "gpirt_b200_chol_lower", "gpirt_b200_dgemm", "gpirt_b200_dgemm_i8",
     "gpirt_b200_trsm_lower", "gpirt_b200_ll_bar", "gpirt_b200_fp64_peak_tflops", "gpirt_b200_rng_probe",
 ]
 
@@ -80,6 +80,8 @@ def load():
     L.gpirt_b200_chol_lower.argtypes = [_dp, C.c_int64]
     L.gpirt_b200_dgemm.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double, _dp, C.c_int64, _dp,
                                    C.c_int64, C.c_double, _dp, C.c_int64, C.c_int]
+    L.gpirt_b200_dgemm_i8.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp,
+                                      C.c_int64, C.c_int, _dp]
     L.gpirt_b200_trsm_lower.argtypes = [C.c_int, C.c_int64, C.c_int64, _dp, _dp]
     L.gpirt_b200_ll_bar.argtypes = [_dp, _dp, _dp, C.c_int64, C.c_int64, _dp]
     L.gpirt_b200_fp64_peak_tflops.argtypes = [_dp, _dp]

@@ -2,7 +2,10 @@
 // and the FP64 peak microbenchmark used as the tensor-roofline denominator.
 #include <vector>
 
+#include <climits>
+
 #include "gemm_f64.cuh"
+#include "dgemm_i8.cuh"
 #include "kernels.cuh"
 #include "linalg.cuh"
 
@@ -124,6 +127,46 @@ int gpirt_b200_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alp
     g.alpha = alpha; g.beta = beta; g.tri = tri;
     GP_TRY(gemm_f64(0, ta != 0, tb != 0, g));
     GP_CUDA(cudaDeviceSynchronize());
+    return d2h(C, ldc, c.p, ldc, M, N);
+}
+
+int gpirt_b200_dgemm_i8(int ta, int a_lower, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double* C, int64_t ldc, int reps, double* ms) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || (ta && a_lower)) return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    if (M == 0 || N == 0) return GPIRT_B200_OK;
+    const int64_t ar = ta ? K : M, ac = ta ? M : K;
+    DevBuf a, b, c;
+    GP_TRY(a.alloc(lda * ac)); GP_TRY(b.alloc(ldb * N)); GP_TRY(c.alloc(ldc * N));
+    GP_TRY(h2d(a.p, lda, A, lda, ar, ac)); GP_TRY(h2d(b.p, ldb, B, ldb, K, N));
+    GP_CUDA(cudaMemset(c.p, 0, (size_t)ldc * N * sizeof(double)));
+    DigitPlanes pa, pb;
+    int rc = pa.init(0, (int)M, (int)K, 128);
+    if (rc == GPIRT_B200_OK) rc = pb.init(0, (int)N, (int)K, 64);
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    for (auto& e : ev) if (rc == GPIRT_B200_OK && cudaEventCreate(&e) != cudaSuccess) rc = GPIRT_B200_ERR_CUDA;
+    const int R = (reps > 0 && ms) ? reps : 1;
+    float t_slice = 0.f, t_mm = 0.f;
+    if (rc == GPIRT_B200_OK) {
+        cudaEventRecord(ev[0], 0);
+        for (int it = 0; it < R && rc == GPIRT_B200_OK; ++it) {
+            rc = ta ? pa.slice_kcontig(0, a.p, lda) : pa.slice_mcontig(0, a.p, lda, a_lower != 0, 0, (int)K, INT_MIN);
+            if (rc == GPIRT_B200_OK) rc = pb.slice_kcontig(0, b.p, ldb);
+        }
+        cudaEventRecord(ev[1], 0);
+        for (int it = 0; it < R && rc == GPIRT_B200_OK; ++it)
+            rc = dgemm_i8(0, pa, pb, c.p, ldc, a_lower != 0, 0, (int)K, false, a_lower ? 24 : 18);
+        cudaEventRecord(ev[2], 0);
+        if (rc == GPIRT_B200_OK && cudaDeviceSynchronize() != cudaSuccess) {
+            set_last_error("dgemm_i8 failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = GPIRT_B200_ERR_CUDA;
+        }
+        if (rc == GPIRT_B200_OK) { cudaEventElapsedTime(&t_slice, ev[0], ev[1]); cudaEventElapsedTime(&t_mm, ev[1], ev[2]); }
+    }
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    pa.destroy(); pb.destroy();
+    if (rc) return rc;
+    if (ms) { ms[0] = t_mm / R; ms[1] = t_slice / R; }
     return d2h(C, ldc, c.p, ldc, M, N);
 }
 

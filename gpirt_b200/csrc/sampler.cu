@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "linalg.cuh"
 #include "theta_int8.cuh"
+#include "dgemm_i8.cuh"
 
 namespace gpirt {
 
@@ -61,11 +62,15 @@ struct gpirt_b200_sampler {
     CholLookahead lookahead;
     ThetaInt8 ti8;               // tcgen05 int8 path of the theta contraction (no missing data)
     bool use_ti8 = false;
+    // the two big FP64 products (nu = L Z, f* = A^T f) in 56-bit fixed point on the int8 tensor cores (dgemm_i8.cu):
+    // digit planes of L, of A = S^-1 K* and of the item-side operand (Z before the ESS, f after it: never both alive)
+    DigitPlanes dp_L, dp_A, dp_B;
+    bool use_i8gemm = false;
+    int lz_group = 4;            // finished Cholesky panels per slice of the pipelined L Z product
     // sweep pipelining: the latency-bound Cholesky chain of sweep t overlaps (a) the beta step of sweep t, (b) the Philox
     // fill of Z for sweep t+1 and (c) the product nu = L Z of sweep t+1, accumulated block column by block column behind
-    // the factorisation (each group of LZ_GROUP finished panels contributes nu[r0:, :] += L[r0:, r0:r1] Z[r0:r1, :])
+    // the factorisation (each group of lz_group finished panels contributes nu[r0:, :] += L[r0:, r0:r1] Z[r0:r1, :])
     bool pipeline = true;
-    static constexpr int LZ_GROUP = 4;
     cudaStream_t st_beta = nullptr, st_lz = nullptr;
     cudaEvent_t ev_theta = nullptr, ev_z = nullptr, ev_beta = nullptr, ev_lz = nullptr;
     bool nu_ready = false;       // nu already holds L z for sweep nu_sweep
@@ -247,6 +252,19 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     }
     has_missing = cnt[0] != 0;
     if (use_ti8) GP_TRY(ti8.init(stream, y8, ldy8, n, m, has_missing));
+    {   // GPIRT_GEMM_INT8 = 1 / 0 forces the fixed-point tensor-core products on / off (FP64 DMMA instead)
+        const char* e = getenv("GPIRT_GEMM_INT8");
+        use_i8gemm = e ? atoi(e) != 0 : (n >= 512 && m >= 256);
+        if (n > 65536) use_i8gemm = false;   // int32 accumulators hold 8 x 64 x 64 x K
+        if (use_i8gemm) {
+            GP_TRY(dp_L.init(stream, n, n, 128));
+            GP_TRY(dp_A.init(stream, N_GRID, n, 128));
+            GP_TRY(dp_B.init(stream, m, n, 64));
+            lz_group = 8;
+        }
+        const char* g = getenv("GPIRT_LZ_GROUP");
+        if (g && atoi(g) > 0) lz_group = atoi(g);
+    }
     GP_TRY(step_rebuild());                                                         // gpirtMCMC.cpp:15-17
     GP_CUDA(cudaStreamSynchronize(stream));
     return check_status();
@@ -278,6 +296,11 @@ int gpirt_b200_sampler::step_rebuild() {
     return GPIRT_B200_OK;
 }
 
+// |L_ik| <= sqrt(K_ii) = sqrt(1.001) < 2: one fixed scale for every row of L, so L can be sliced while later panels of
+// the factorisation are still running
+constexpr int L_FIXED_EXP = 1;
+constexpr int LZ_GROUP_COLS = 24, FSTAR_GROUP_COLS = 18;   // column tiles per L2-resident group (dgemm_i8)
+
 static GemmArgs G(int M, int N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                   double alpha, double beta, int tri, int b_abs = 0) {
     GemmArgs g;
@@ -293,7 +316,13 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
     GP_TRY(launch_fill_normal(stream, Z, n, m, ldn, k, sweep == 0 ? P_INIT_F_Z : P_ESS_Z, item_offset));
     toc();
     tic(GPIRT_B200_T_LZ_GEMM);   // nu_j = cholS z_j for all items in one product (mvnormal.h:10)
-    GP_TRY(gemm_f64(stream, false, false, G(n, m, n, L, ldn, Z, ldn, sweep == 0 ? f : nu, ldn, 1.0, 0.0, TRI_A_LOWER)));
+    if (use_i8gemm) {
+        GP_TRY(dp_L.slice_mcontig(stream, L, ldn, true, 0, n, L_FIXED_EXP));
+        GP_TRY(dp_B.slice_kcontig(stream, Z, ldn));
+        GP_TRY(dgemm_i8(stream, dp_L, dp_B, sweep == 0 ? f : nu, ldn, true, 0, n, false, LZ_GROUP_COLS));
+    } else {
+        GP_TRY(gemm_f64(stream, false, false, G(n, m, n, L, ldn, Z, ldn, sweep == 0 ? f : nu, ldn, 1.0, 0.0, TRI_A_LOWER)));
+    }
     toc();
     if (sweep == 0) return GPIRT_B200_OK;   // initial f_j = rmvnorm(cholS), gpirtMCMC.cpp:19-21
     tic(GPIRT_B200_T_ESS);
@@ -323,6 +352,7 @@ int gpirt_b200_sampler::fstar_solves(cudaStream_t st) {
         GP_TRY(comm_allgather_f64(comm, kstar, (size_t)per * ldn, st));
         GP_TRY(comm_allgather_f64(comm, s, (size_t)per, st));
     }
+    if (use_i8gemm) GP_TRY(dp_A.slice_kcontig(st, kstar, ldn));   // row k of A^T = column k of S^-1 K*
     toc_on(b, st);
     return GPIRT_B200_OK;
 }
@@ -336,7 +366,12 @@ int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
         else GP_TRY(fstar_solves(stream));
         solve_ready = false;
         tic(GPIRT_B200_T_FSTAR_GEMM);
-        GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, f, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
+        if (use_i8gemm) {
+            GP_TRY(dp_B.slice_kcontig(stream, f, ldn));
+            GP_TRY(dgemm_i8(stream, dp_A, dp_B, fstar, ldN, false, 0, n, false, FSTAR_GROUP_COLS));
+        } else {
+            GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, f, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
+        }
         toc();
     } else {
         solve_ready = false;
@@ -429,7 +464,7 @@ int gpirt_b200_sampler::ess_only(uint32_t sweep) {
 // End of sweep `sweep` with the next sweep's proposals prepared under the factorisation:
 //   st_beta : Z(next) = Philox normals, then the beta step                                   (needs the new theta only)
 //   stream  : K(theta,theta)+1e-3 I, right-looking Cholesky chain (+ its bulk stream), L^-1
-//   st_lz   : after every LZ_GROUP finished block columns  nu[r0:, :] (+)= L[r0:, r0:r1] Z[r0:r1, :]
+//   st_lz   : after every lz_group finished block columns  nu[r0:, :] (+)= L[r0:, r0:r1] Z[r0:r1, :]
 int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     static const int mask = getenv("GPIRT_PIPE_MASK") ? atoi(getenv("GPIRT_PIPE_MASK")) : 7;   // debugging: 1 LZ, 2 beta/fill, 4 solves
     cudaStream_t st_beta = (mask & 2) ? this->st_beta : stream;
@@ -452,17 +487,30 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     toc();
     bool first = true;
     lookahead.after_panel = [&](int k, int nblk, cudaEvent_t done) -> int {
-        if ((k + 1) % LZ_GROUP != 0 && k != nblk - 1) return GPIRT_B200_OK;
-        const int g = k / LZ_GROUP;
-        const int r0 = g * LZ_GROUP * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
-        if (first) { GP_CUDA(cudaStreamWaitEvent(st_lz, ev_z, 0)); first = false; }
+        if ((k + 1) % lz_group != 0 && k != nblk - 1) return GPIRT_B200_OK;
+        const int g = k / lz_group;
+        const int r0 = g * lz_group * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
+        if (first) {
+            GP_CUDA(cudaStreamWaitEvent(st_lz, ev_z, 0));
+            if (use_i8gemm) {
+                Seg sz = tic_on(GPIRT_B200_T_LZ_GEMM, st_lz);
+                GP_TRY(dp_B.slice_kcontig(st_lz, Z, ldn));
+                toc_on(sz, st_lz);
+            }
+            first = false;
+        }
         GP_CUDA(cudaStreamWaitEvent(st_lz, done, 0));
         Seg sg = tic_on(GPIRT_B200_T_LZ_GEMM, st_lz);
-        GemmArgs a;
-        a.M = n - r0; a.N = m; a.K = r1 - r0;
-        a.A = L + r0 + (int64_t)r0 * ldn; a.lda = ldn; a.B = Z + r0; a.ldb = ldn; a.C = nu + r0; a.ldc = ldn;
-        a.alpha = 1.0; a.beta = (g == 0) ? 0.0 : 1.0; a.tri = TRI_A_LOWER;
-        GP_TRY(gemm_f64(st_lz, false, false, a));
+        if (use_i8gemm) {
+            GP_TRY(dp_L.slice_mcontig(st_lz, L, ldn, true, r0, r1, L_FIXED_EXP));
+            GP_TRY(dgemm_i8(st_lz, dp_L, dp_B, nu, ldn, true, r0, r1, g != 0, LZ_GROUP_COLS, false));
+        } else {
+            GemmArgs a;
+            a.M = n - r0; a.N = m; a.K = r1 - r0;
+            a.A = L + r0 + (int64_t)r0 * ldn; a.lda = ldn; a.B = Z + r0; a.ldb = ldn; a.C = nu + r0; a.ldc = ldn;
+            a.alpha = 1.0; a.beta = (g == 0) ? 0.0 : 1.0; a.tri = TRI_A_LOWER;
+            GP_TRY(gemm_f64(st_lz, false, false, a));
+        }
         toc_on(sg, st_lz);
         if (k == nblk - 1) GP_CUDA(cudaEventRecord(ev_lz, st_lz));
         return GPIRT_B200_OK;
@@ -516,6 +564,7 @@ void gpirt_b200_sampler::destroy() {
     for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
+    dp_L.destroy(); dp_A.destroy(); dp_B.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
                     kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, panel_scratch};
     for (void* p : ptrs) pool_free(p, stream);

@@ -186,6 +186,20 @@ def dgemm(A, B, C_=None, alpha=1.0, beta=0.0, ta=False, tb=False, tri=0):
     return Cm
 
 
+def dgemm_i8(A, B, ta=False, a_lower=False, reps=0):
+    """op(A) @ B in 56-bit fixed point on the int8 tensor cores (the sampler's L·Z / f* product kernel).
+    reps > 0: also returns (kernel ms, slicing ms)"""
+    A = _F(A); B = _F(B)
+    M = A.shape[1] if ta else A.shape[0]
+    K = A.shape[0] if ta else A.shape[1]
+    N = B.shape[1]
+    Cm = np.zeros((M, N), order="F")
+    ms = np.zeros(2)
+    _lib.check(_lib.load().gpirt_b200_dgemm_i8(int(ta), int(a_lower), M, N, K, _lib.ptr(A), max(1, A.shape[0]), _lib.ptr(B),
+                                               max(1, B.shape[0]), _lib.ptr(Cm), max(1, M), int(reps), _lib.ptr(ms)))
+    return (Cm, ms) if reps > 0 else Cm
+
+
 def trsm_lower(L, B, trans=False):
     """solve(trimatl(L), B) / solve(trimatu(L.t()), B) — src/draw-fstar.cpp:7,19"""
     L = _F(L); B = np.array(B, dtype=np.float64, order="F", copy=True)

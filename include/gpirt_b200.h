@@ -138,6 +138,12 @@ int gpirt_b200_chol_lower(double* S, int64_t n);
  * 1 = A lower-triangular (skip structurally-zero k blocks), 2 = only the lower triangle of C is written */
 int gpirt_b200_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri);
+/* C = op(A) B in 56-bit fixed point on the int8 tensor cores (tcgen05; the path the sampler uses for L Z and for the f*
+ * product): ta = 0: A is M x K, ta = 1: A is K x M; B is K x N; a_lower (ta = 0 only): A is lower triangular.
+ * reps > 0 and ms != NULL: the product is repeated and the mean kernel time (CUDA events) is returned in ms[0],
+ * operand slicing in ms[1].  |error| <= K 2^-51 max|A[i,:]| max|B[:,j]| */
+int gpirt_b200_dgemm_i8(int ta, int a_lower, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda,
+                        const double* B, int64_t ldb, double* C, int64_t ldc, int reps, double* ms);
 /* solve L X = B (trans = 0) or L^T X = B (trans = 1) in place, L n x n lower, B n x nrhs (arma::solve(trimatl/u)) */
 int gpirt_b200_trsm_lower(int trans, int64_t n, int64_t nrhs, const double* L, double* B);
 /* ll_bar for every column: out[j] = -sum_i log(1+exp(-y_ij (f_ij + mu_ij))), src/log-likelihood.cpp:25-37 */
