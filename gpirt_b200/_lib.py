@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpirt_b200.so")
+LIB_PATH = os.environ.get("GPIRT_B200_LIB") or os.path.join(HERE, "libgpirt_b200.so")   # override: development A/B builds
 N_GRID = 1001
 
 # every symbol include/gpirt_b200.h declares (tests check the .so exports exactly these)

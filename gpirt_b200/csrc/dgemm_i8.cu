@@ -30,15 +30,26 @@ namespace gpirt {
 namespace {
 
 constexpr int DG_S = DigitPlanes::S;
-constexpr int DG_BM = 128, DG_BN = 64, DG_KB = 64, DG_UMMA_K = 32;
+#ifndef DG_KB_BYTES
+#define DG_KB_BYTES 64
+#endif
+constexpr int DG_BM = 128, DG_BN = 64, DG_KB = DG_KB_BYTES, DG_UMMA_K = 32;
 constexpr int DG_A_PLANE = DG_BM * DG_KB, DG_B_PLANE = DG_BN * DG_KB;
 constexpr int DG_A_BYTES = DG_S * DG_A_PLANE, DG_B_BYTES = DG_S * DG_B_PLANE, DG_STAGE_BYTES = DG_A_BYTES + DG_B_BYTES;
-constexpr int DG_STAGES = 2;
+constexpr int DG_STAGES = 196608 / DG_STAGE_BYTES;
 constexpr int DG_SMEM = DG_STAGES * DG_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int DG_TMEM_COLS = 512;
 constexpr int DG_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer (+ TMEM alloc), warps 2..5: epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a converged warp; ptxas recognises the pattern and emits the tensor-core / TMA instructions of the elected
+// region back to back (a `lane == 0` branch instead wraps every one of them in a per-thread election loop, which made
+// instruction issue — not the tensor pipe — the limit of this kernel)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -66,20 +77,50 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // start address >> 4 | SBO (8 rows x 64 B = 512 B) >> 4 at bit 32 | version 1 at bit 46 | SWIZZLE_64B (4) at bit 61
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
     uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)((8 * DG_KB) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
+    d |= (uint64_t)(DG_KB == 64 ? 4 : 6) << 61;
     return d;
 }
 // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t DG_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DG_BN >> 3) << 17) | ((uint32_t)(DG_BM >> 4) << 24);
 
+// collector usage of the A operand: the tensor core keeps the A slab it has just read (fill / use) so that the next MMAs
+// on the same slab (use / lastuse) do not read it from shared memory again — with a 128 x 64 tile the operand reads
+// (A 4 KB + B 2 KB per MMA) would otherwise exceed the shared-memory bandwidth
+enum { COLL_NONE = 0, COLL_FILL = 1, COLL_USE = 2, COLL_LASTUSE = 3 };
+template <int COLL>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(DG_IDESC), "r"(accumulate) : "memory");
+    if constexpr (COLL == COLL_FILL)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(DG_IDESC), "r"(accumulate) : "memory");
+    else if constexpr (COLL == COLL_USE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(DG_IDESC), "r"(accumulate) : "memory");
+    else if constexpr (COLL == COLL_LASTUSE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(DG_IDESC), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(DG_IDESC), "r"(accumulate) : "memory");
+}
+// all products of A plane P with B planes 0 .. S-1-P (levels P .. S-1), A read from shared memory once
+template <int P, int T = 0>
+__device__ __forceinline__ void umma_plane_row(uint32_t tmem_base, uint64_t da, uint32_t sb, uint32_t acc_rest, uint32_t acc_p0) {
+    constexpr int LAST = DG_S - 1 - P;
+    constexpr int COLL = (LAST == 0) ? COLL_NONE : (T == 0 ? COLL_FILL : (T == LAST ? COLL_LASTUSE : COLL_USE));
+    umma_i8<COLL>(tmem_base + (uint32_t)((P + T) * DG_BN), da, umma_desc_sw64(sb + T * DG_B_PLANE), P == 0 ? acc_p0 : acc_rest);
+    if constexpr (T < LAST) umma_plane_row<P, T + 1>(tmem_base, da, sb, acc_rest, acc_p0);
+}
+template <int P = 0>
+__device__ __forceinline__ void umma_all_planes(uint32_t tmem_base, uint32_t sa, uint32_t sb, uint32_t first) {
+    // level l is first written by the pair (A plane 0, B plane l): only those MMAs may overwrite
+    umma_plane_row<P>(tmem_base, umma_desc_sw64(sa + P * DG_A_PLANE), sb, 1u, first);
+    if constexpr (P + 1 < DG_S) umma_all_planes<P + 1>(tmem_base, sa, sb, first);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -128,7 +169,8 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // K-block range of a row tile: a lower-triangular A stops at the diagonal block
     auto kb_end = [&](int r) { return a_lower ? min(kb_hi, (int)(((int64_t)(r + 1) * DG_BM + DG_KB - 1) / DG_KB)) : kb_hi; };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+        if (elect_one()) {
         // ---- TMA producer ----
         uint32_t it = 0;
         for (int o = blockIdx.x; o < sched.total; o += gridDim.x) {
@@ -147,7 +189,9 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
         // ---- MMA issuer ----
         uint32_t it = 0, tile_it = 0;
         for (int o = blockIdx.x; o < sched.total; o += gridDim.x, ++tile_it) {
@@ -162,20 +206,12 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * DG_STAGE_BYTES), sb = sa + DG_A_BYTES;
 #pragma unroll
-                for (int k2 = 0; k2 < DG_KB / DG_UMMA_K; ++k2) {
-                    const uint32_t first = (uint32_t)((kb != kb_lo) | (k2 != 0));
-#pragma unroll
-                    for (int l = 0; l < DG_S; ++l) {
-#pragma unroll
-                        for (int p = 0; p <= l; ++p)
-                            umma_i8(tmem_base + (uint32_t)(l * DG_BN),
-                                    umma_desc_sw64(sa + p * DG_A_PLANE + k2 * DG_UMMA_K),
-                                    umma_desc_sw64(sb + (l - p) * DG_B_PLANE + k2 * DG_UMMA_K), first | (uint32_t)(p != 0));
-                    }
-                }
+                for (int k2 = 0; k2 < DG_KB / DG_UMMA_K; ++k2)
+                    umma_all_planes(tmem_base, sa + k2 * DG_UMMA_K, sb + k2 * DG_UMMA_K, (uint32_t)((kb != kb_lo) | (k2 != 0)));
                 umma_commit(empty0 + 8 * s);   // frees the shared-memory slot once these MMAs have read it
             }
             umma_commit(tfull);                // all level accumulators of this tile are complete
+        }
         }
     } else if (warp >= 2) {
         // ---- epilogue: TMEM -> registers, Horner over the 8 levels in FP64, scale, store ----
@@ -356,7 +392,7 @@ int make_map_sw64(CUtensorMap* map, void* base, uint64_t rows, uint64_t row_byte
     const cuuint32_t box[2] = {(cuuint32_t)DG_KB, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    DG_KB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GPIRT_B200_ERR_CUDA; }
     return GPIRT_B200_OK;
 }

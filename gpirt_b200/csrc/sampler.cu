@@ -260,7 +260,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
             GP_TRY(dp_L.init(stream, n, n, 128));
             GP_TRY(dp_A.init(stream, N_GRID, n, 128));
             GP_TRY(dp_B.init(stream, m, n, 64));
-            lz_group = 8;
+            lz_group = 16;
         }
         const char* g = getenv("GPIRT_LZ_GROUP");
         if (g && atoi(g) > 0) lz_group = atoi(g);

@@ -31,6 +31,12 @@ constexpr int TI_SMEM = TI_STAGES * TI_STAGE_BYTES + 1024 /* alignment slack */ 
 constexpr int TI_TMEM_COLS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a converged warp (ptxas then emits the TMA / tensor-core instructions of the region back to back)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -100,8 +106,9 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ---- TMA producer ----
+        if (elect_one())
         for (int kb = 0; kb < num_kblocks; ++kb) {
             const int s = kb % TI_STAGES;
             const uint32_t ph = (uint32_t)(kb / TI_STAGES) & 1u;
@@ -111,7 +118,8 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_load_2d(sa, &tmA, kb * TI_BK, m_tile * TI_BM, full0 + 8 * s);
             tma_load_2d(sb, &tmB, kb * TI_BK, n_tile * TI_BN, full0 + 8 * s);
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+        if (elect_one()) {
         // ---- MMA issuer: one thread drives the tensor core for the whole CTA ----
         for (int kb = 0; kb < num_kblocks; ++kb) {
             const int s = kb % TI_STAGES;
@@ -126,6 +134,7 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             umma_commit(empty0 + 8 * s);   // frees the shared-memory slot once these MMAs have read it
         }
         umma_commit(tfull);                // accumulator complete
+        }
     } else if (warp >= 4) {
         // ---- epilogue: TMEM -> registers, combine the 8 digit planes of each grid point, FP64 store ----
         mbar_wait(tfull, 0);

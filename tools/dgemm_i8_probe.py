@@ -27,13 +27,14 @@ def check(M, N, K, ta, lower, seed=0):
 
 if __name__ == "__main__":
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-    check(128, 64, 64, False, False)
-    check(128, 64, 128, True, False)
-    check(100, 37, 50, False, False)
-    check(300, 200, 257, True, False)
-    check(257, 130, 257, False, True)
-    check(1000, 333, 1000, False, True)
-    check(1001, 500, 1100, True, False)
+    if not (len(sys.argv) > 1 and sys.argv[1] == "bench"):
+        check(128, 64, 64, False, False)
+        check(128, 64, 128, True, False)
+        check(100, 37, 50, False, False)
+        check(300, 200, 257, True, False)
+        check(257, 130, 257, False, True)
+        check(1000, 333, 1000, False, True)
+        check(1001, 500, 1100, True, False)
     if not quick:
         n, m = 4096, 10000
         rs = np.random.RandomState(1)
