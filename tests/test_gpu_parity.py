@@ -64,6 +64,44 @@ def test_dgemm(G, ta, tb, M, N, K):
     assert np.max(np.abs(got0 - (A.T if ta else A) @ (B.T if tb else B))) <= 1e-13 * scale
 
 
+@pytest.mark.parametrize("ta,lower,M,N,K", [(0, 0, 1, 1, 1), (0, 0, 128, 64, 64), (1, 0, 100, 37, 50), (1, 0, 300, 200, 257),
+                                             (0, 1, 257, 130, 257), (0, 1, 1000, 333, 1000), (1, 0, 1001, 500, 1100),
+                                             (0, 0, 129, 65, 4097)])
+def test_dgemm_i8_fixed_point_tensor_core_product(G, ta, lower, M, N, K):
+    """op(A) B in 56-bit fixed point on the int8 tensor cores (tcgen05): the kernel behind nu = L Z (draw-f.cpp:20) and the
+    f* product.  The plane products are exact integers, so the only error is the dropped digit levels:
+    |err_ij| <= K 2^-51 max|A[i,:]| max|B[:,j]|  (the tolerance stated in include/gpirt_b200.h)"""
+    rs = np.random.RandomState(M * 11 + N * 5 + K)
+    A = rs.randn(M, K) * np.exp(2.0 * rs.randn(M, 1))          # rows of very different magnitude
+    B = rs.randn(K, N) * np.exp(2.0 * rs.randn(1, N))
+    if lower:
+        A = np.tril(A)
+    if M > 2:
+        A[1, :] = 0.0                                            # an all-zero row
+    if K > 3:
+        A[0, 3] = 0.0
+    got = G.dgemm_i8(np.asfortranarray(A.T) if ta else A, B, ta=bool(ta), a_lower=bool(lower))
+    want = A @ B
+    bound = K * 2.0 ** -51 * np.abs(A).max(axis=1)[:, None] * np.abs(B).max(axis=0)[None, :]
+    assert np.all(np.abs(got - want) <= bound + 1e-300)
+    # against an FP64 product's own error scale: within a few units of K u sum|a||b| when rows are evenly scaled
+    A2 = np.tril(rs.randn(M, K)) if lower else rs.randn(M, K)
+    B2 = rs.randn(K, N)
+    got2 = G.dgemm_i8(np.asfortranarray(A2.T) if ta else A2, B2, ta=bool(ta), a_lower=bool(lower))
+    assert np.max(np.abs(got2 - A2 @ B2)) <= 64 * 2.0 ** -53 * max(1.0, np.max(np.abs(A2) @ np.abs(B2)))
+
+
+def test_dgemm_i8_is_deterministic_and_matches_dmma(G):
+    rs = np.random.RandomState(3)
+    L = np.tril(rs.randn(700, 700)) / 30.0
+    Z = rs.randn(700, 900)
+    a = G.dgemm_i8(L, Z, a_lower=True)
+    b = G.dgemm_i8(L, Z, a_lower=True)
+    assert np.array_equal(a, b), "integer accumulation: bit-identical from run to run"
+    assert np.array_equal(G.dgemm_i8(L, Z[:, 100:300], a_lower=True), a[:, 100:300]), "columns are independent (item sharding)"
+    assert np.max(np.abs(a - G.dgemm(L, Z, None, tri=1))) <= 1e-13
+
+
 @pytest.mark.parametrize("n,m", [(100, 37), (300, 300), (1100, 1300)])
 def test_dgemm_triangular_modes(G, n, m):
     rs = np.random.RandomState(n)
@@ -266,9 +304,10 @@ def test_step_draw_beta(G, O, n, m, missing):
 # lock-step chains: the whole sampler against the oracle's gpirtMCMC restatement, same seed
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,m,S,B,mode", [(2, 1, 1, 1, 0), (5, 3, 2, 0, 0), (30, 10, 3, 2, 0), (30, 10, 3, 2, 1), (100, 40, 2, 1, 0),
-                                          (257, 33, 2, 0, 0), (400, 150, 3, 1, 0), (400, 150, 2, 1, 1)])
+                                          (257, 33, 2, 0, 0), (400, 150, 3, 1, 0), (400, 150, 2, 1, 1), (640, 300, 2, 1, 0)])
 def test_lockstep_chain(G, O, n, m, S, B, mode):
-    prob = make_problem(n, m, seed=n + 11, missing=0.08 if n != 400 else 0.0)   # n = 400: pipelined sweep + int8 theta path
+    # n = 400: pipelined sweep + int8 theta path;  n = 640: also the fixed-point tensor-core products for L Z and f*
+    prob = make_problem(n, m, seed=n + 11, missing=0.08 if n not in (400, 640) else 0.0)
     seed = 4242 + n
     from gpirt_b200 import ResponseMatrix
     got = G.gpirtMCMC(ResponseMatrix(prob["y"]), S, B, beta_prior_means=prob["pm"], beta_prior_sds=prob["psd"],
@@ -282,6 +321,22 @@ def test_lockstep_chain(G, O, n, m, S, B, mode):
     assert np.max(np.abs(got["beta"] - want["beta"])) <= 1e-9
     assert np.max(np.abs(got["f"] - want["f"])) <= 1e-7
     assert np.max(np.abs(got["IRFs"] - want["IRFs"])) <= 1e-7
+
+
+def test_chain_fixed_point_products_match_dmma_products(G, monkeypatch):
+    """the same chain with nu = L Z and the f* product on the int8 tensor cores (dgemm_i8.cu) and on FP64 DMMA"""
+    from gpirt_b200 import ResponseMatrix
+    prob = make_problem(700, 320, seed=99, missing=0.05)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GPIRT_GEMM_INT8", flag)
+        out[flag] = G.gpirtMCMC(ResponseMatrix(prob["y"]), 4, 2, beta_prior_means=prob["pm"], beta_prior_sds=prob["psd"],
+                                beta_proposal_sds=prob["pstep"], theta_init=prob["theta"], seed=77)
+    a, b = out["1"], out["0"]
+    assert np.array_equal(a["theta"], b["theta"])
+    assert np.max(np.abs(a["beta"] - b["beta"])) <= 1e-10
+    assert np.max(np.abs(a["f"] - b["f"])) <= 1e-9
+    assert np.max(np.abs(a["IRFs"] - b["IRFs"])) <= 1e-9
 
 
 def test_senate116_short_chain(G, O):
