@@ -132,7 +132,8 @@ int gpirt_b200_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alp
 
 int gpirt_b200_dgemm_i8(int ta, int a_lower, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* C, int64_t ldc, int reps, double* ms) {
-    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || (ta && a_lower)) return GPIRT_B200_ERR_ARG;
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0 || (ta && a_lower == 1) || (!ta && a_lower == 2) || a_lower < 0 || a_lower > 2)
+        return GPIRT_B200_ERR_ARG;
     GP_TRY(have_device());
     if (M == 0 || N == 0) return GPIRT_B200_OK;
     const int64_t ar = ta ? K : M, ac = ta ? M : K;
@@ -150,12 +151,12 @@ int gpirt_b200_dgemm_i8(int ta, int a_lower, int64_t M, int64_t N, int64_t K, co
     if (rc == GPIRT_B200_OK) {
         cudaEventRecord(ev[0], 0);
         for (int it = 0; it < R && rc == GPIRT_B200_OK; ++it) {
-            rc = ta ? pa.slice_kcontig(0, a.p, lda) : pa.slice_mcontig(0, a.p, lda, a_lower != 0, 0, (int)K, INT_MIN);
+            rc = ta ? pa.slice_kcontig(0, a.p, lda) : pa.slice_mcontig(0, a.p, lda, a_lower == 1, 0, (int)K, INT_MIN);
             if (rc == GPIRT_B200_OK) rc = pb.slice_kcontig(0, b.p, ldb);
         }
         cudaEventRecord(ev[1], 0);
         for (int it = 0; it < R && rc == GPIRT_B200_OK; ++it)
-            rc = dgemm_i8(0, pa, pb, c.p, ldc, a_lower != 0, 0, (int)K, false, a_lower ? 24 : 18);
+            rc = dgemm_i8(0, pa, pb, c.p, ldc, a_lower, 0, (int)K, false, a_lower ? 24 : 18);
         cudaEventRecord(ev[2], 0);
         if (rc == GPIRT_B200_OK && cudaDeviceSynchronize() != cudaSuccess) {
             set_last_error("dgemm_i8 failed: %s", cudaGetErrorString(cudaGetLastError()));

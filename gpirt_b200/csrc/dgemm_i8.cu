@@ -127,20 +127,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 struct TileSched {
-    int mtiles, ntiles, group_cols, total;
+    int mtiles, ntiles, group_cols, total, ascending;   // ascending: row tile 0 is the heaviest (upper-triangular A)
     // order index -> (row tile, column tile): column tiles in groups whose planes stay in L2, row tiles heaviest first
     __device__ __forceinline__ void at(int o, int& r, int& c) const {
         const int per_group = group_cols * mtiles;
         const int g = o / per_group, o2 = o - g * per_group;
         const int gw = min(group_cols, ntiles - g * group_cols);
-        r = mtiles - 1 - o2 / gw;
+        r = ascending ? o2 / gw : mtiles - 1 - o2 / gw;
         c = g * group_cols + o2 % gw;
     }
 };
 
 __global__ void __launch_bounds__(DG_THREADS, 1)
 k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TileSched sched,
-           int a_rows_pad, int b_rows_pad, int kb_lo, int kb_hi, int a_lower, int M, int N,
+           int a_rows_pad, int b_rows_pad, int kb_lo, int kb_hi, int a_tri, int M, int N,
            const double* __restrict__ ascale, const double* __restrict__ bscale, double* __restrict__ C, int64_t ldc,
            int accumulate) {
     extern __shared__ uint8_t smem_raw[];
@@ -166,8 +166,9 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // K-block range of a row tile: a lower-triangular A stops at the diagonal block
-    auto kb_end = [&](int r) { return a_lower ? min(kb_hi, (int)(((int64_t)(r + 1) * DG_BM + DG_KB - 1) / DG_KB)) : kb_hi; };
+    // K-block range of a row tile: a lower-triangular A stops at the diagonal block, an upper-triangular one starts there
+    auto kb_end = [&](int r) { return a_tri == 1 ? min(kb_hi, (int)(((int64_t)(r + 1) * DG_BM + DG_KB - 1) / DG_KB)) : kb_hi; };
+    auto kb_begin = [&](int r) { return a_tri == 2 ? max(kb_lo, (int)(((int64_t)r * DG_BM) / DG_KB)) : kb_lo; };
 
     if (warp == 0) {
         if (elect_one()) {
@@ -177,7 +178,7 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             int r, c;
             sched.at(o, r, c);
             const int ke = kb_end(r);
-            for (int kb = kb_lo; kb < ke; ++kb, ++it) {
+            for (int kb = kb_begin(r); kb < ke; ++kb, ++it) {
                 const uint32_t s = it % DG_STAGES, ph = (it / DG_STAGES) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 mbar_expect_tx(full0 + 8 * s, DG_STAGE_BYTES);
@@ -197,17 +198,17 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int o = blockIdx.x; o < sched.total; o += gridDim.x, ++tile_it) {
             int r, c;
             sched.at(o, r, c);
-            const int ke = kb_end(r);
+            const int ke = kb_end(r), kb0 = kb_begin(r);
             mbar_wait(tempty, (tile_it & 1u) ^ 1u);          // epilogue has drained the previous tile's accumulators
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = kb_lo; kb < ke; ++kb, ++it) {
+            for (int kb = kb0; kb < ke; ++kb, ++it) {
                 const uint32_t s = it % DG_STAGES, ph = (it / DG_STAGES) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * DG_STAGE_BYTES), sb = sa + DG_A_BYTES;
 #pragma unroll
                 for (int k2 = 0; k2 < DG_KB / DG_UMMA_K; ++k2)
-                    umma_all_planes(tmem_base, sa + k2 * DG_UMMA_K, sb + k2 * DG_UMMA_K, (uint32_t)((kb != kb_lo) | (k2 != 0)));
+                    umma_all_planes(tmem_base, sa + k2 * DG_UMMA_K, sb + k2 * DG_UMMA_K, (uint32_t)((kb != kb0) | (k2 != 0)));
                 umma_commit(empty0 + 8 * s);   // frees the shared-memory slot once these MMAs have read it
             }
             umma_commit(tfull);                // all level accumulators of this tile are complete
@@ -225,7 +226,7 @@ k_dgemm_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const double sa_i = (i < M) ? ascale[i] : 0.0;
             mbar_wait(tfull, tile_it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (kb_end(r) > kb_lo) {
+            if (kb_end(r) > kb_begin(r)) {
 #pragma unroll 1
                 for (int cc = 0; cc < DG_BN / 8; ++cc) {
                     uint32_t v[DG_S][8];
@@ -447,7 +448,7 @@ void DigitPlanes::destroy() {
     delete map; map = nullptr;
 }
 
-int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double* C, int64_t ldc, bool a_lower, int k_lo,
+int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double* C, int64_t ldc, int a_tri, int k_lo,
              int k_hi, bool accumulate, int group_cols, bool persistent) {
     if (A.rows <= 0 || B.rows <= 0) return GPIRT_B200_OK;
     if (!A.map || !B.map || A.k_pad != B.k_pad || A.box_rows != DG_BM || B.box_rows != DG_BN || k_lo % DG_KB != 0 || k_lo < 0 ||
@@ -469,13 +470,14 @@ int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double
     sched.ntiles = (int)(B.rows_pad / DG_BN);
     sched.group_cols = group_cols > 0 ? min(group_cols, sched.ntiles) : sched.ntiles;
     sched.total = sched.mtiles * sched.ntiles;
+    sched.ascending = a_tri == DG_TRI_UPPER ? 1 : 0;
     // persistent (one CTA per SM walks the tile list) when the kernel owns the GPU; one tile per CTA when it shares the
     // GPU with a latency-critical chain on a higher-priority stream, so that the chain's CTAs get SMs as tiles retire
     static const int force = getenv("GPIRT_I8_PERSISTENT") ? atoi(getenv("GPIRT_I8_PERSISTENT")) : -1;
     const bool pers = force >= 0 ? force != 0 : persistent;
     const int grid = pers ? min(sched.total, n_sm) : sched.total;
     GP_LAUNCH(k_dgemm_i8, (unsigned)grid, DG_THREADS, DG_SMEM, st, A.map->m, B.map->m, sched, (int)A.rows_pad, (int)B.rows_pad,
-              k_lo / DG_KB, (int)ceil_div(k_hi, DG_KB), a_lower ? 1 : 0, A.rows, B.rows, A.scale, B.scale, C, ldc, accumulate ? 1 : 0);
+              k_lo / DG_KB, (int)ceil_div(k_hi, DG_KB), a_tri, A.rows, B.rows, A.scale, B.scale, C, ldc, accumulate ? 1 : 0);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
 }

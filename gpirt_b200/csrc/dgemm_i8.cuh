@@ -32,8 +32,11 @@ struct DigitPlanes {
 };
 
 // C[i + j ldc] (+)= sum_{k in [k_lo, k_hi)} A[i, k] B[j, k]    i < A.rows, j < B.rows
-// a_lower: A[i, k] = 0 for k > i (row tiles stop at the diagonal).  group_cols: column tiles per L2-resident group.
-int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double* C, int64_t ldc, bool a_lower,
+// a_tri: DG_TRI_LOWER: A[i, k] = 0 for k > i (row tiles stop at the diagonal block); DG_TRI_UPPER: A[i, k] = 0 for k < i
+// (row tiles start there) — the planes must hold zeros in the skipped part.  group_cols: column tiles per L2-resident
+// group (0: one group).
+enum { DG_TRI_NONE = 0, DG_TRI_LOWER = 1, DG_TRI_UPPER = 2 };
+int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double* C, int64_t ldc, int a_tri,
              int k_lo, int k_hi, bool accumulate, int group_cols, bool persistent = true);
 
 }  // namespace gpirt

@@ -13,6 +13,8 @@
 #include "gemm_f64.cuh"
 #include "kernels.cuh"
 #include "linalg.cuh"
+#include <climits>
+
 #include "theta_int8.cuh"
 #include "dgemm_i8.cuh"
 
@@ -65,6 +67,7 @@ struct gpirt_b200_sampler {
     // the two big FP64 products (nu = L Z, f* = A^T f) in 56-bit fixed point on the int8 tensor cores (dgemm_i8.cu):
     // digit planes of L, of A = S^-1 K* and of the item-side operand (Z before the ESS, f after it: never both alive)
     DigitPlanes dp_L, dp_A, dp_B;
+    DigitPlanes dp_Linv, dp_LinvT, dp_K;   // L^-1 by rows, by columns (= rows of L^-T), and this rank's K* / L^-1 K* columns
     bool use_i8gemm = false;
     int lz_group = 4;            // finished Cholesky panels per slice of the pipelined L Z product
     // sweep pipelining: the latency-bound Cholesky chain of sweep t overlaps (a) the beta step of sweep t, (b) the Philox
@@ -260,6 +263,12 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
             GP_TRY(dp_L.init(stream, n, n, 128));
             GP_TRY(dp_A.init(stream, N_GRID, n, 128));
             GP_TRY(dp_B.init(stream, m, n, 64));
+            if (opts.fstar_mode == 0) {
+                const int per = (int)ceil_div(N_GRID, comm.world), c0 = min(N_GRID, comm.rank * per), nc = min(N_GRID, c0 + per) - c0;
+                GP_TRY(dp_Linv.init(stream, n, n, 128));
+                GP_TRY(dp_LinvT.init(stream, n, n, 128));
+                if (nc > 0) GP_TRY(dp_K.init(stream, nc, n, 64));
+            }
             lz_group = 16;
         }
         const char* g = getenv("GPIRT_LZ_GROUP");
@@ -319,7 +328,7 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
     if (use_i8gemm) {
         GP_TRY(dp_L.slice_mcontig(stream, L, ldn, true, 0, n, L_FIXED_EXP));
         GP_TRY(dp_B.slice_kcontig(stream, Z, ldn));
-        GP_TRY(dgemm_i8(stream, dp_L, dp_B, sweep == 0 ? f : nu, ldn, true, 0, n, false, LZ_GROUP_COLS));
+        GP_TRY(dgemm_i8(stream, dp_L, dp_B, sweep == 0 ? f : nu, ldn, DG_TRI_LOWER, 0, n, false, LZ_GROUP_COLS));
     } else {
         GP_TRY(gemm_f64(stream, false, false, G(n, m, n, L, ldn, Z, ldn, sweep == 0 ? f : nu, ldn, 1.0, 0.0, TRI_A_LOWER)));
     }
@@ -343,7 +352,18 @@ int gpirt_b200_sampler::fstar_solves(cudaStream_t st) {
     GP_TRY(launch_se_cov(st, theta, n, theta_star + c0, nc, 0.0, false, kstar + (int64_t)c0 * ldn, ldn));   // :17
     toc_on(a, st);
     Seg b = tic_on(GPIRT_B200_T_TRSM, st);
-    if (nc > 0) {
+    if (nc > 0 && use_i8gemm) {
+        // the two triangular products with L^-1 in fixed point as well (L^-1 has zeros above the diagonal: trtri_lower)
+        double* Kc = kstar + (int64_t)c0 * ldn;
+        double* K2c = kstar2 + (int64_t)c0 * ldn;
+        GP_TRY(dp_Linv.slice_mcontig(st, Linv, ldn, true, 0, n, INT_MIN));
+        GP_TRY(dp_LinvT.slice_kcontig(st, Linv, ldn));
+        GP_TRY(dp_K.slice_kcontig(st, Kc, ldn));
+        GP_TRY(dgemm_i8(st, dp_Linv, dp_K, K2c, ldn, DG_TRI_LOWER, 0, n, false, 0));      // :19
+        GP_TRY(launch_fstar_sd(st, K2c, ldn, n, nc, s + c0));                             // :20
+        GP_TRY(dp_K.slice_kcontig(st, K2c, ldn));
+        GP_TRY(dgemm_i8(st, dp_LinvT, dp_K, Kc, ldn, DG_TRI_UPPER, 0, n, false, 0));
+    } else if (nc > 0) {
         GP_TRY(gemm_f64(st, false, false, G(n, nc, n, Linv, ldn, kstar + (int64_t)c0 * ldn, ldn, kstar2 + (int64_t)c0 * ldn, ldn, 1.0, 0.0, TRI_A_LOWER)));   // :19
         GP_TRY(launch_fstar_sd(st, kstar2 + (int64_t)c0 * ldn, ldn, n, nc, s + c0));           // :20
         GP_TRY(gemm_f64(st, true, false, G(n, nc, n, Linv, ldn, kstar2 + (int64_t)c0 * ldn, ldn, kstar + (int64_t)c0 * ldn, ldn, 1.0, 0.0, TRI_A_UPPER)));
@@ -368,7 +388,7 @@ int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
         tic(GPIRT_B200_T_FSTAR_GEMM);
         if (use_i8gemm) {
             GP_TRY(dp_B.slice_kcontig(stream, f, ldn));
-            GP_TRY(dgemm_i8(stream, dp_A, dp_B, fstar, ldN, false, 0, n, false, FSTAR_GROUP_COLS));
+            GP_TRY(dgemm_i8(stream, dp_A, dp_B, fstar, ldN, DG_TRI_NONE, 0, n, false, FSTAR_GROUP_COLS));
         } else {
             GP_TRY(gemm_f64(stream, true, false, G(N, m, n, kstar, ldn, f, ldn, fstar, ldN, 1.0, 0.0, TRI_NONE)));
         }
@@ -503,7 +523,7 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         Seg sg = tic_on(GPIRT_B200_T_LZ_GEMM, st_lz);
         if (use_i8gemm) {
             GP_TRY(dp_L.slice_mcontig(st_lz, L, ldn, true, r0, r1, L_FIXED_EXP));
-            GP_TRY(dgemm_i8(st_lz, dp_L, dp_B, nu, ldn, true, r0, r1, g != 0, LZ_GROUP_COLS, false));
+            GP_TRY(dgemm_i8(st_lz, dp_L, dp_B, nu, ldn, DG_TRI_LOWER, r0, r1, g != 0, LZ_GROUP_COLS, false));
         } else {
             GemmArgs a;
             a.M = n - r0; a.N = m; a.K = r1 - r0;
@@ -564,7 +584,7 @@ void gpirt_b200_sampler::destroy() {
     for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
-    dp_L.destroy(); dp_A.destroy(); dp_B.destroy();
+    dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
     void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
                     kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, panel_scratch};
     for (void* p : ptrs) pool_free(p, stream);

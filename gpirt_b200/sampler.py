@@ -186,9 +186,10 @@ def dgemm(A, B, C_=None, alpha=1.0, beta=0.0, ta=False, tb=False, tri=0):
     return Cm
 
 
-def dgemm_i8(A, B, ta=False, a_lower=False, reps=0):
+def dgemm_i8(A, B, ta=False, a_lower=0, reps=0):
     """op(A) @ B in 56-bit fixed point on the int8 tensor cores (the sampler's L·Z / f* product kernel).
-    reps > 0: also returns (kernel ms, slicing ms)"""
+    a_lower: 1 = A lower triangular (ta False), 2 = A^T upper triangular (ta True).  reps > 0: also returns
+    (kernel ms, slicing ms)"""
     A = _F(A); B = _F(B)
     M = A.shape[1] if ta else A.shape[0]
     K = A.shape[0] if ta else A.shape[1]

@@ -139,7 +139,8 @@ int gpirt_b200_chol_lower(double* S, int64_t n);
 int gpirt_b200_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int tri);
 /* C = op(A) B in 56-bit fixed point on the int8 tensor cores (tcgen05; the path the sampler uses for L Z and for the f*
- * product): ta = 0: A is M x K, ta = 1: A is K x M; B is K x N; a_lower (ta = 0 only): A is lower triangular.
+ * product): ta = 0: A is M x K, ta = 1: A is K x M; B is K x N; a_lower = 1 (ta = 0 only): op(A) is lower triangular,
+ * a_lower = 2 (ta = 1 only): op(A) = A^T is upper triangular and the strict upper triangle of the stored A holds zeros.
  * reps > 0 and ms != NULL: the product is repeated and the mean kernel time (CUDA events) is returned in ms[0],
  * operand slicing in ms[1].  |error| <= K 2^-51 max|A[i,:]| max|B[:,j]| */
 int gpirt_b200_dgemm_i8(int ta, int a_lower, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda,

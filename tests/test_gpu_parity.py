@@ -91,6 +91,18 @@ def test_dgemm_i8_fixed_point_tensor_core_product(G, ta, lower, M, N, K):
     assert np.max(np.abs(got2 - A2 @ B2)) <= 64 * 2.0 ** -53 * max(1.0, np.max(np.abs(A2) @ np.abs(B2)))
 
 
+@pytest.mark.parametrize("n,N", [(64, 3), (300, 70), (1000, 1001)])
+def test_dgemm_i8_upper_triangular_transposed_operand(G, n, N):
+    """op(A) = A^T with A stored lower triangular (the L^-T product of draw-fstar.cpp:24): row tiles start at the diagonal"""
+    rs = np.random.RandomState(n)
+    A = np.tril(rs.randn(n, n)) * np.exp(rs.randn(1, n))
+    B = rs.randn(n, N)
+    got = G.dgemm_i8(A, B, ta=True, a_lower=2)
+    want = A.T @ B
+    bound = n * 2.0 ** -51 * np.abs(A).max(axis=0)[:, None] * np.abs(B).max(axis=0)[None, :]
+    assert np.all(np.abs(got - want) <= bound + 1e-300)
+
+
 def test_dgemm_i8_is_deterministic_and_matches_dmma(G):
     rs = np.random.RandomState(3)
     L = np.tril(rs.randn(700, 700)) / 30.0
