@@ -251,6 +251,15 @@ def main():
             "chol": ("tensor", n ** 3 / 3.0), "trtri": ("tensor", n ** 3 / 3.0),
             "trsm": ("tensor", 2.0 * n * n * N_GRID if args.fstar_mode == 0 else n * n * N_GRID + 2.0 * n * n * m_loc),
             "ess": ("hbm", 25.0 * n * m_loc), "beta": ("hbm", 17.0 * n * m_loc), "kbuild": ("hbm", 4.0 * n * n)}
+    fixed_point = s.uses(1) == 1
+    fp64_flops = {k: work[k][1] for k in ("lz_gemm", "fstar_gemm", "trsm")}
+    if fixed_point:
+        # these three segments run as 36 exact int8 plane-pair products on tcgen05 (dgemm_i8.cu): the work the tensor
+        # pipe executes is 36 x the FP64 product's multiply-adds
+        work["lz_gemm"] = ("tensor_i8", 36.0 * fp64_flops["lz_gemm"])
+        work["fstar_gemm"] = ("tensor_i8", 36.0 * fp64_flops["fstar_gemm"])
+        if args.fstar_mode == 0:
+            work["trsm"] = ("tensor_i8", 36.0 * fp64_flops["trsm"])
     dom = max(work, key=lambda k: timers[k][0])
     bound, alg = work[dom]
     dom_ms = timers[dom][0] / K                      # per sweep (a segment may be several launches, e.g. L Z in groups)
@@ -258,7 +267,17 @@ def main():
     dmma, dfma = G.fp64_peak_tflops()
     fp64_src = ("FP64 tensor pipe (DMMA.8x8x4) issue-rate microbenchmark measured in this run; "
                 "MEASURED_PEAKS.json has no FP64 figure")
-    if bound == "tensor":
+    i8_note = None
+    if bound == "tensor_i8":
+        # tcgen05 kind::i8 issues twice the multiply-adds per instruction of kind::f16 (K = 32 vs 16), so the int8
+        # ceiling is 2 x the measured dense bf16 figure (sustained: the kernel runs inside a long step)
+        bf16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        achieved, peak, unit = alg / dom_ms * 1e-9, 2.0 * bf16, "TFLOP/s"
+        peak_src = "2 x dense bf16 (%s, sustained) = int8 tensor ops/s; nominal int8 dense is 4500" % peak_src
+        i8_note = {"fp64_equivalent_tflops": fp64_flops[dom] / dom_ms * 1e-9, "fp64_tensor_peak_tflops": dmma,
+                   "plane_pair_products": 36, "frac_of_nominal_int8": alg / dom_ms * 1e-9 / 4500.0}
+        bound = "tensor"
+    elif bound == "tensor":
         achieved, peak, unit, peak_src = alg / dom_ms * 1e-9, dmma, "TFLOP/s", fp64_src
     else:
         achieved, peak, unit = alg / dom_ms * 1e-6, peaks["hbm_gbs"], "GB/s"
@@ -272,6 +291,10 @@ def main():
     s.set_pipeline(True)
     iso_ms = t_iso[dom][0] / Ki
     iso = alg / iso_ms * (1e-9 if bound == "tensor" else 1e-6)
+    iso_peak = peak
+    if i8_note is not None:
+        iso_peak = 2.0 * peaks["bf16_tflops"]       # timed alone: the burst figure
+        i8_note["fp64_equivalent_tflops_isolated"] = fp64_flops[dom] / iso_ms * 1e-9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tp):
@@ -285,7 +308,9 @@ def main():
                 "ms_per_sweep": dom_ms, "share_of_step": dom_ms / (ms / K),
                 "note": "timed region runs pipelined: the L Z product and the beta step execute UNDER the Cholesky chain, so "
                         "their event durations include co-running kernels; `isolated` repeats the measurement with pipelining off",
-                "isolated": {"achieved": iso, "frac": iso / peak, "ms_per_sweep": iso_ms, "sweep_ms_unpipelined": ms_iso / Ki},
+                "isolated": {"achieved": iso, "peak": iso_peak, "frac": iso / iso_peak, "ms_per_sweep": iso_ms,
+                             "sweep_ms_unpipelined": ms_iso / Ki},
+                "fixed_point": i8_note,
                 "per_step_ms": {k: v[0] / K for k, v in timers.items() if v[1]},
                 "per_step_ms_isolated": {k: v[0] / Ki for k, v in t_iso.items() if v[1]}}
     s.close()

@@ -140,8 +140,8 @@ int launch_rng_probe(cudaStream_t st, RngKey key, uint32_t purpose, uint32_t str
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ESS_ITER_CAP = 10000;
 
-template <int EPT>
-__global__ void __launch_bounds__(512) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
                       int64_t ldy, const double* __restrict__ theta, const double* __restrict__ beta, int n, RngKey key,
                       uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status,
                       const double* __restrict__ sp) {
@@ -247,7 +247,10 @@ __global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, con
 
 // block size / elements-per-thread for a per-item CTA holding n <= 4096 respondents in registers (ept = 0: stream)
 static void item_cta_shape(int n, int& ept, int& threads) {
-    if (n <= 256) ept = 1; else if (n <= 1024) ept = 2; else if (n <= 2048) ept = 4; else if (n <= 4096) ept = 8; else ept = 0;
+    // 2048 < n <= 4096: 512 threads x 8 values.  GPIRT_ITEM_THREADS=1024 selects 1024 x 4 (32 warps per SM instead of
+    // 16): measured 10% SLOWER at n = 4096 — the kernels are bound by the L1 gather of table rows, not by latency.
+    static const int wide = getenv("GPIRT_ITEM_THREADS") ? atoi(getenv("GPIRT_ITEM_THREADS")) : 512;
+    if (n <= 256) ept = 1; else if (n <= 1024) ept = 2; else if (n <= 2048) ept = 4; else if (n <= 4096) ept = (wide > 512 ? 4 : 8); else ept = 0;
     threads = ept ? (int)round_up(ceil_div(n, ept), 32) : 1024;
     if (threads < 32) threads = 32;
 }
@@ -261,10 +264,13 @@ int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const i
     const double* sp = nullptr;
     GP_TRY(softplus_table(&sp));
     switch (ept) {
-        case 1: GP_LAUNCH(k_ess<1>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
-        case 2: GP_LAUNCH(k_ess<2>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
-        case 4: GP_LAUNCH(k_ess<4>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
-        case 8: GP_LAUNCH(k_ess<8>, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        case 1: GP_LAUNCH((k_ess<1, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        case 2: GP_LAUNCH((k_ess<2, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
+        case 4:
+            if (threads > 512) GP_LAUNCH((k_ess<4, 1024>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp);
+            else GP_LAUNCH((k_ess<4, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp);
+            break;
+        case 8: GP_LAUNCH((k_ess<8, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
         default: GP_LAUNCH(k_ess_stream, m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
     }
     GP_CUDA(cudaGetLastError());
@@ -468,8 +474,8 @@ __device__ __forceinline__ double dnorm_log(double x, double mu, double sd) {  /
     return -(0.918938533204672741780329736406 + 0.5 * t * t + log(sd));
 }
 
-template <int EPT>
-__global__ void __launch_bounds__(512) k_beta(double* __restrict__ beta, const double* __restrict__ f, int64_t ld, const int8_t* __restrict__ y8,
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_beta(double* __restrict__ beta, const double* __restrict__ f, int64_t ld, const int8_t* __restrict__ y8,
                        int64_t ldy, const double* __restrict__ theta, const double* __restrict__ pm,
                        const double* __restrict__ psd, const double* __restrict__ pstep, int n, RngKey key,
                        uint32_t item_offset, const double* __restrict__ sp) {
@@ -555,10 +561,13 @@ int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, cons
     const double* sp = nullptr;
     GP_TRY(softplus_table(&sp));
     switch (ept) {
-        case 1: GP_LAUNCH(k_beta<1>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
-        case 2: GP_LAUNCH(k_beta<2>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
-        case 4: GP_LAUNCH(k_beta<4>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
-        case 8: GP_LAUNCH(k_beta<8>, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        case 1: GP_LAUNCH((k_beta<1, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        case 2: GP_LAUNCH((k_beta<2, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
+        case 4:
+            if (threads > 512) GP_LAUNCH((k_beta<4, 1024>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp);
+            else GP_LAUNCH((k_beta<4, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp);
+            break;
+        case 8: GP_LAUNCH((k_beta<8, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
         default: GP_LAUNCH(k_beta_stream, m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
     }
     GP_CUDA(cudaGetLastError());

@@ -836,6 +836,12 @@ int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled) {
 }
 
 int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s) { return s ? g_launch_count - s->launches_at_create : 0; }
+int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature) {
+    if (!s) return -1;
+    if (feature == 0) return s->use_ti8 ? 1 : 0;
+    if (feature == 1) return s->use_i8gemm ? 1 : 0;
+    return -1;
+}
 
 void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s) {
     if (!s) return;

@@ -147,6 +147,10 @@ class Sampler:
     def launches(self):
         return int(_lib.load().gpirt_b200_sampler_launches(self.h))
 
+    def uses(self, feature):
+        """1 if this sampler runs feature 0 (int8 theta contraction) / 1 (fixed-point tensor-core products)"""
+        return int(_lib.load().gpirt_b200_sampler_uses(self.h, int(feature)))
+
     def close(self):
         if self.h:
             _lib.load().gpirt_b200_sampler_destroy(self.h)

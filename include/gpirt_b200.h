@@ -127,6 +127,9 @@ int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled); /* per-st
  * Z fill and L Z product (identical draws either way; off gives un-overlapped per-kernel timings) */
 int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled);
 int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s); /* kernels launched by this sampler so far */
+/* which tensor-core path this sampler selected: feature 0 = int8 theta contraction, 1 = fixed-point (int8) L Z / f* /
+ * K*-solve products; returns 1 / 0, or -1 for an unknown feature (bench.py picks the roofline denominator by it) */
+int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature);
 void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s);
 
 /* ---- single operations on HOST buffers (each replaces one reference function; used by the parity tests) ---- */
