@@ -1,6 +1,8 @@
 // The resident GP-IRT Gibbs sampler: device state + one sweep = the reference's loop body
 // (src/gpirtMCMC.cpp:68-78 / :87-97) as a fixed sequence of kernel launches on one stream, and gpirt_b200_mcmc(),
 // the drop-in for gpirtMCMC() (src/gpirtMCMC.cpp:5-117).
+#include <sys/mman.h>
+
 #include <cstdarg>
 #include <algorithm>
 #include <atomic>
@@ -257,7 +259,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     if (use_ti8) GP_TRY(ti8.init(stream, y8, ldy8, n, m, has_missing));
     {   // GPIRT_GEMM_INT8 = 1 / 0 forces the fixed-point tensor-core products on / off (FP64 DMMA instead)
         const char* e = getenv("GPIRT_GEMM_INT8");
-        use_i8gemm = e ? atoi(e) != 0 : (n >= 512 && m >= 256);
+        use_i8gemm = e ? atoi(e) != 0 : (n >= 512 && std::max<int64_t>(m, opts.m_global) >= 256);   // same path on every shard
         if (n > 65536) use_i8gemm = false;   // int32 accumulators hold 8 x 64 x 64 x K
         if (use_i8gemm) {
             GP_TRY(dp_L.init(stream, n, n, 128));
@@ -881,6 +883,13 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     const int S1 = sample_iterations + 1;
     const size_t nm = (size_t)n * m;
+    if (keep_f && !getenv("GPIRT_NO_HUGEPAGE_HINT")) {
+        // the caller's f array is fresh pageable memory: ask for transparent huge pages on its interior so that the
+        // first-touch faults of the draw stores are 2 MiB each instead of 4 KiB (advisory; ignored where THP is off)
+        const uintptr_t a = ((uintptr_t)f_out + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
+        const uintptr_t b = ((uintptr_t)f_out + (size_t)S1 * nm * sizeof(double)) & ~(((uintptr_t)2 << 20) - 1);
+        if (b > a) madvise((void*)a, b - a, MADV_HUGEPAGE);
+    }
     std::vector<double> small((size_t)n + 2 * (size_t)m);
     GP_CUDA(cudaStreamCreateWithFlags(&gd.copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {

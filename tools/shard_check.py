@@ -22,7 +22,7 @@ if rank == 0:
     uid_t = torch.tensor(list(G.nccl_unique_id()), dtype=torch.uint8, device="cuda")
 dist.broadcast(uid_t, 0)
 uid = bytes(uid_t.cpu().tolist())
-n, m, S, B = 300, 90, 3, 2
+n, m, S, B = int(os.environ.get("SHARD_N", "300")), int(os.environ.get("SHARD_M", "90")), 3, 2
 missing = float(os.environ.get("SHARD_MISSING", "0.05"))
 p = make_problem(n, m, seed=5, missing=missing)
 per = (m + world - 1) // world
