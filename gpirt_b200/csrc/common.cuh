@@ -59,15 +59,14 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // Sum over the whole block; every thread gets the same value.  `buf` = 32 doubles of shared memory that no other
-// phase is touching between the two barriers (callers alternate between two buffers to save a barrier).
+// phase is touching between the two barriers (callers alternate between two buffers to save a barrier).  The warp
+// partials are combined by the same shuffle tree in every warp (fixed order: deterministic, identical in all threads).
 __device__ __forceinline__ double block_sum(double v, double* buf) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     if (lane == 0) buf[w] = v;
     __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < nw; ++i) t += buf[i];
-    return t;
+    return warp_sum(lane < nw ? buf[lane] : 0.0);
 }
 
 // The reference's per-observation log-likelihood term, src/log-likelihood.cpp:19-20 / :33-34:

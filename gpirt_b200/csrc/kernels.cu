@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const doub
                       uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status,
                       const double* __restrict__ sp) {
     __shared__ double red[2][32];
+    __shared__ double nxt[2][4];   // speculative next proposal: angle, sine, cosine (double-buffered like red)
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const uint32_t item = item_offset + (uint32_t)j;
     const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
@@ -173,9 +174,21 @@ __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const doub
     eps_min = eps - TWO_PI;                                                          // :36 (eps_max stays 2 pi)
     int iter = 0;
     double s, c;
+    sincos(eps, &s, &c);
+    // The angle of proposal t+1 does not depend on the likelihood of proposal t, only on its being rejected: the shrunk
+    // bracket, the next Philox uniform, the next angle and its sine / cosine are computed by warp 0 WHILE proposal t is
+    // evaluated and published through shared memory ahead of the barrier of the block sum, so the serial part of a
+    // round is the reduction alone.  Same formulas, same bits as the sequential loop.
+    const bool leader = tid < 32;
     for (;;) {
         iter += 1;
-        sincos(eps, &s, &c);
+        const double emin_n = (eps < 0.0) ? eps : eps_min, emax_n = (eps < 0.0) ? eps_max : eps;   // :50-55 if rejected
+        if (leader) {
+            const double eps_n = emin_n + (emax_n - emin_n) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);  // :56
+            double sn, cn;
+            sincos(eps_n, &sn, &cn);
+            if (tid == 0) { nxt[iter & 1][0] = eps_n; nxt[iter & 1][1] = sn; nxt[iter & 1][2] = cn; }
+        }
         part = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
@@ -185,8 +198,8 @@ __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const doub
             }
         const double ll_new = block_sum(part, red[iter & 1]);
         if (ll_new > log_y) break;                                                   // :45 strict
-        if (eps < 0.0) eps_min = eps; else eps_max = eps;                            // :50-55
-        eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);  // :56
+        eps_min = emin_n; eps_max = emax_n;
+        eps = nxt[iter & 1][0]; s = nxt[iter & 1][1]; c = nxt[iter & 1][2];
         if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }    // NaN likelihood: reference would spin
     }
 #pragma unroll
@@ -245,6 +258,132 @@ __global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, con
     if (tid == 0 && nprop) nprop[j] = iter;
 }
 
+
+// ---- persistent variant ---------------------------------------------------------------------------------------------
+// One CTA per SM walks the item list (next item claimed with an atomic counter, so the data-dependent proposal counts
+// balance themselves) and the NEXT item's f, nu and y columns are fetched into shared memory with cp.async while the
+// current item's shrink loop runs: with one register-heavy CTA per SM the HBM latency of every item's loads was fully
+// exposed (ncu: a quarter of all stall samples sat on the first use of the loaded columns).  theta is read once per
+// CTA.  Same arithmetic, same bits as k_ess.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_ess_persist(double* __restrict__ f, const double* __restrict__ nu, int64_t ld,
+                                                      const int8_t* __restrict__ y8, int64_t ldy, const double* __restrict__ theta,
+                                                      const double* __restrict__ beta, int n, int m, RngKey key,
+                                                      uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status,
+                                                      const double* __restrict__ sp, int* __restrict__ work) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ double red[2][32];
+    __shared__ double nxt[2][4];
+    __shared__ int s_next;
+    const int tid = threadIdx.x, T = blockDim.x, NP = EPT * T;
+    double* fbuf = reinterpret_cast<double*>(dsm);
+    double* nbuf = fbuf + 2 * NP;
+    int8_t* ybuf = reinterpret_cast<int8_t*>(nbuf + 2 * NP);
+    double th[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) { const int i = tid + e * T; th[e] = (i < n) ? theta[i] : 0.0; }
+    auto prefetch = [&](int j, int b) {
+        const double* fs = f + (int64_t)j * ld;
+        const double* ns = nu + (int64_t)j * ld;
+        const int8_t* ys = y8 + (int64_t)j * ldy;
+        for (int c = tid; c < (n + 1) / 2; c += T) {
+            cp_async16(fbuf + b * NP + 2 * c, fs + 2 * c);
+            cp_async16(nbuf + b * NP + 2 * c, ns + 2 * c);
+        }
+        for (int c = tid; c < (n + 15) / 16; c += T) cp_async16(ybuf + b * NP + 16 * c, ys + 16 * c);
+        cp_async_commit();
+    };
+    int j = blockIdx.x, b = 0;
+    if (j < m) prefetch(j, 0);
+    while (j < m) {
+        if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);
+        __syncthreads();
+        const int jn = s_next;
+        if (jn < m) { prefetch(jn, b ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const uint32_t item = item_offset + (uint32_t)j;
+        const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
+        double fv[EPT], nv[EPT], gm[EPT], yv[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = tid + e * T;
+            if (i < n) {
+                fv[e] = fbuf[b * NP + i];
+                nv[e] = nbuf[b * NP + i];
+                yv[e] = (double)ybuf[b * NP + i];
+                gm[e] = fma(th[e], b1, b0);
+            } else { fv[e] = nv[e] = gm[e] = yv[e] = 0.0; }
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+            if (yv[e] != 0.0) part -= ll_term_fast(sp, yv[e] * (fv[e] + gm[e]));
+        const double ll_cur = block_sum(part, red[0]);
+        const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));          // draw-f.cpp:28-29
+        const double TWO_PI = 6.283185307179586476925286766559;
+        double eps_min = 0.0, eps_max = TWO_PI;                                          // :33-34
+        double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u); // :35
+        eps_min = eps - TWO_PI;                                                          // :36
+        int iter = 0;
+        double s, c;
+        sincos(eps, &s, &c);
+        const bool leader = tid < 32;
+        for (;;) {
+            iter += 1;
+            const double emin_n = (eps < 0.0) ? eps : eps_min, emax_n = (eps < 0.0) ? eps_max : eps;   // :50-55 if rejected
+            if (leader) {
+                const double eps_n = emin_n + (emax_n - emin_n) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);  // :56
+                double sn, cn;
+                sincos(eps_n, &sn, &cn);
+                if (tid == 0) { nxt[iter & 1][0] = eps_n; nxt[iter & 1][1] = sn; nxt[iter & 1][2] = cn; }
+            }
+            part = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (yv[e] != 0.0) {
+                    const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
+                    part -= ll_term_fast(sp, yv[e] * (fp + gm[e]));
+                }
+            const double ll_new = block_sum(part, red[iter & 1]);
+            if (ll_new > log_y) break;                                                   // :45 strict
+            eps_min = emin_n; eps_max = emax_n;
+            eps = nxt[iter & 1][0]; s = nxt[iter & 1][1]; c = nxt[iter & 1][2];
+            if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = tid + e * T;
+            if (i < n) f[i + (int64_t)j * ld] = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));
+        }
+        if (tid == 0 && nprop) nprop[j] = iter;
+        j = jn;
+        b ^= 1;
+    }
+}
+
+// persistent grid: as many CTAs as fit the device at once (never more than there are items)
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem, int m, int* grid) {
+    int dev = 0, sms = 0, per_sm = 0;
+    GP_CUDA(cudaGetDevice(&dev));
+    GP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) { set_last_error("per-item kernel does not fit on an SM"); return GPIRT_B200_ERR_CUDA; }
+    *grid = std::min(m, sms * per_sm);
+    return GPIRT_B200_OK;
+}
+static bool item_kernels_persistent() {
+    static const int v = getenv("GPIRT_ITEM_PERSIST") ? atoi(getenv("GPIRT_ITEM_PERSIST")) : 1;
+    return v != 0;
+}
+
 // block size / elements-per-thread for a per-item CTA holding n <= 4096 respondents in registers (ept = 0: stream)
 static void item_cta_shape(int n, int& ept, int& threads) {
     // 2048 < n <= 4096: 512 threads x 8 values.  GPIRT_ITEM_THREADS=1024 selects 1024 x 4 (32 warps per SM instead of
@@ -255,14 +394,34 @@ static void item_cta_shape(int n, int& ept, int& threads) {
     if (threads < 32) threads = 32;
 }
 
+#define ESS_PERSIST_CASE(E, MT)                                                                                              \
+    {                                                                                                                            \
+        const size_t smem = (size_t)2 * (E) * threads * 17;                                                                      \
+        int grid = 0;                                                                                                            \
+        GP_TRY(persistent_grid(k_ess_persist<E, MT>, threads, smem, m, &grid));                                                  \
+        GP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));                                                                      \
+        GP_LAUNCH((k_ess_persist<E, MT>), grid, threads, smem, st, f, nu, ld, y8, ldy, theta, beta, n, m, key, item_offset, nprop, \
+                  status, sp, work);                                                                                             \
+    }
+
 int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const int8_t* y8, int64_t ldy,
                const double* theta, const double* beta, int n, int m, RngKey key, uint32_t item_offset, int* nprop,
-               int* status) {
+               int* status, int* work) {
     if (m <= 0) return GPIRT_B200_OK;
     int ept, threads;
     item_cta_shape(n, ept, threads);
     const double* sp = nullptr;
     GP_TRY(softplus_table(&sp));
+    if (work && ept && item_kernels_persistent()) {
+        switch (ept) {
+            case 1: ESS_PERSIST_CASE(1, 512) break;
+            case 2: ESS_PERSIST_CASE(2, 512) break;
+            case 4: if (threads > 512) ESS_PERSIST_CASE(4, 1024) else ESS_PERSIST_CASE(4, 512) break;
+            default: ESS_PERSIST_CASE(8, 512) break;
+        }
+        GP_CUDA(cudaGetLastError());
+        return GPIRT_B200_OK;
+    }
     switch (ept) {
         case 1: GP_LAUNCH((k_ess<1, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
         case 2: GP_LAUNCH((k_ess<2, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;

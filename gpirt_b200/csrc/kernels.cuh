@@ -23,7 +23,7 @@ int launch_init_beta(cudaStream_t st, double* beta, const double* pm, const doub
 // elliptical slice sampler for all items (draw-f.cpp); f updated in place
 int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const int8_t* y8, int64_t ldy,
                const double* theta, const double* beta, int n, int m, RngKey key, uint32_t item_offset, int* nprop,
-               int* status);
+               int* status, int* work = nullptr);   // work: one zeroable int (item counter of the persistent variant)
 // s_k = 1 - sqrt(sum_i tmp_ik^2)
 int launch_fstar_sd(cudaStream_t st, const double* tmp, int64_t ld, int n, int N, double* s);
 // f*_kj = (mean_kj + beta0_j + beta1_j theta*_k) + s_k z_kj, in place over mean; optional IRF accumulation

@@ -93,6 +93,7 @@ struct gpirt_b200_sampler {
            *psd = nullptr, *pstep = nullptr, *L = nullptr, *Dinv = nullptr, *f = nullptr, *Z = nullptr, *nu = nullptr,
            *fstar = nullptr, *Dmat = nullptr, *irf_sum = nullptr, *kstar = nullptr, *s = nullptr, *logPt = nullptr,
            *partial = nullptr, *Linv = nullptr, *Tmp = nullptr, *kstar2 = nullptr, *panel_scratch = nullptr;
+    int* work = nullptr;   // item counters of the persistent per-item kernels: [0] ESS, [1] beta
     int *nprop = nullptr, *theta_idx = nullptr, *status = nullptr;  // status[0] chol, [1] ess, [2] theta-degenerate count
     unsigned long long* counters = nullptr;                        // [0] missing cells, [1] illegal cells
     static constexpr int N_CHUNKS = 32;
@@ -228,7 +229,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
     GP_TRY(alloc(kstar, (size_t)ldn * (N_GRID + 8))); GP_TRY(alloc(s, (size_t)ldN));
     GP_TRY(alloc(logPt, (size_t)ldN * (n + 1))); GP_TRY(alloc(partial, (size_t)N_CHUNKS * N_GRID));
-    GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2));
+    GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2)); GP_TRY(alloc(work, 4));
     GP_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int), stream));
     GP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream));
     GP_CUDA(cudaMemsetAsync(irf_sum, 0, Nm * sizeof(double), stream));
@@ -337,7 +338,7 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
     toc();
     if (sweep == 0) return GPIRT_B200_OK;   // initial f_j = rmvnorm(cholS), gpirtMCMC.cpp:19-21
     tic(GPIRT_B200_T_ESS);
-    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, k, item_offset, nprop, status + 1));
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, k, item_offset, nprop, status + 1, work));
     toc();
     return GPIRT_B200_OK;
 }
@@ -478,7 +479,7 @@ int gpirt_b200_sampler::init_draws() {
 // ESS with nu already in place (the product L z was accumulated behind the previous sweep's factorisation)
 int gpirt_b200_sampler::ess_only(uint32_t sweep) {
     tic(GPIRT_B200_T_ESS);
-    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1));
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1, work));
     toc();
     return GPIRT_B200_OK;
 }
@@ -587,7 +588,7 @@ void gpirt_b200_sampler::destroy() {
     comm_destroy(comm);
     ti8.destroy();
     dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
-    void* ptrs[] = {y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
+    void* ptrs[] = {work, y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
                     kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, panel_scratch};
     for (void* p : ptrs) pool_free(p, stream);
     if (stream) cudaStreamSynchronize(stream);
