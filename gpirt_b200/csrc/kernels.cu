@@ -1,5 +1,9 @@
 // Non-GEMM kernels of the Gibbs sweep: covariance builder, response ingest, Philox fills, the batched elliptical
 // slice sampler with the fused logistic log-likelihood, f* finishing draw, theta grid sampler, beta Metropolis step.
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "kernels.cuh"
 #include "softplus_table.cuh"
 
@@ -367,16 +371,28 @@ __global__ void __launch_bounds__(MAXT) k_ess_persist(double* __restrict__ f, co
     }
 }
 
-// persistent grid: as many CTAs as fit the device at once (never more than there are items)
+// persistent grid: as many CTAs as fit the device at once; 0 when every item gets its own CTA anyway (then the plain
+// one-CTA-per-item kernel is used).  The occupancy query is cached per (kernel, block size, shared memory, device).
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, int m, int* grid) {
-    int dev = 0, sms = 0, per_sm = 0;
+    struct Key { const void* k; int threads; size_t smem; int dev; bool operator<(const Key& o) const {
+        return std::tie(k, threads, smem, dev) < std::tie(o.k, o.threads, o.smem, o.dev); } };
+    static std::mutex mu;
+    static std::map<Key, int> cache;
+    int dev = 0;
     GP_CUDA(cudaGetDevice(&dev));
-    GP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    if (per_sm < 1) { set_last_error("per-item kernel does not fit on an SM"); return GPIRT_B200_ERR_CUDA; }
-    *grid = std::min(m, sms * per_sm);
+    const Key key{(const void*)kernel, threads, smem, dev};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int sms = 0, per_sm = 0;
+        GP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+        if (per_sm < 1) { set_last_error("per-item kernel does not fit on an SM"); return GPIRT_B200_ERR_CUDA; }
+        it = cache.emplace(key, sms * per_sm).first;
+    }
+    *grid = m > it->second ? it->second : 0;
     return GPIRT_B200_OK;
 }
 static bool item_kernels_persistent() {
@@ -399,9 +415,12 @@ static void item_cta_shape(int n, int& ept, int& threads) {
         const size_t smem = (size_t)2 * (E) * threads * 17;                                                                      \
         int grid = 0;                                                                                                            \
         GP_TRY(persistent_grid(k_ess_persist<E, MT>, threads, smem, m, &grid));                                                  \
-        GP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));                                                                      \
-        GP_LAUNCH((k_ess_persist<E, MT>), grid, threads, smem, st, f, nu, ld, y8, ldy, theta, beta, n, m, key, item_offset, nprop, \
-                  status, sp, work);                                                                                             \
+        if (grid > 0) {                                                                                                          \
+            GP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));                                                                  \
+            GP_LAUNCH((k_ess_persist<E, MT>), grid, threads, smem, st, f, nu, ld, y8, ldy, theta, beta, n, m, key, item_offset,  \
+                      nprop, status, sp, work);                                                                                  \
+            launched = true;                                                                                                     \
+        }                                                                                                                        \
     }
 
 int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const int8_t* y8, int64_t ldy,
@@ -413,6 +432,7 @@ int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const i
     const double* sp = nullptr;
     GP_TRY(softplus_table(&sp));
     if (work && ept && item_kernels_persistent()) {
+        bool launched = false;
         switch (ept) {
             case 1: ESS_PERSIST_CASE(1, 512) break;
             case 2: ESS_PERSIST_CASE(2, 512) break;
@@ -420,7 +440,7 @@ int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const i
             default: ESS_PERSIST_CASE(8, 512) break;
         }
         GP_CUDA(cudaGetLastError());
-        return GPIRT_B200_OK;
+        if (launched) return GPIRT_B200_OK;
     }
     switch (ept) {
         case 1: GP_LAUNCH((k_ess<1, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
@@ -673,6 +693,74 @@ __global__ void __launch_bounds__(MAXT) k_beta(double* __restrict__ beta, const 
     if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
 }
 
+
+// persistent variant of the beta step (see k_ess_persist): next item's f and y columns prefetched, theta read once
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_beta_persist(double* __restrict__ beta, const double* __restrict__ f, int64_t ld,
+                                                       const int8_t* __restrict__ y8, int64_t ldy, const double* __restrict__ theta,
+                                                       const double* __restrict__ pm, const double* __restrict__ psd,
+                                                       const double* __restrict__ pstep, int n, int m, RngKey key,
+                                                       uint32_t item_offset, const double* __restrict__ sp, int* __restrict__ work) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ double red[4][32];
+    __shared__ int s_next;
+    const int tid = threadIdx.x, T = blockDim.x, NP = EPT * T;
+    double* fbuf = reinterpret_cast<double*>(dsm);
+    int8_t* ybuf = reinterpret_cast<int8_t*>(fbuf + 2 * NP);
+    double th[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) { const int i = tid + e * T; th[e] = (i < n) ? theta[i] : 0.0; }
+    auto prefetch = [&](int j, int b) {
+        const double* fs = f + (int64_t)j * ld;
+        const int8_t* ys = y8 + (int64_t)j * ldy;
+        for (int c = tid; c < (n + 1) / 2; c += T) cp_async16(fbuf + b * NP + 2 * c, fs + 2 * c);
+        for (int c = tid; c < (n + 15) / 16; c += T) cp_async16(ybuf + b * NP + 16 * c, ys + 16 * c);
+        cp_async_commit();
+    };
+    int j = blockIdx.x, b = 0;
+    if (j < m) prefetch(j, 0);
+    while (j < m) {
+        if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);
+        __syncthreads();
+        const int jn = s_next;
+        if (jn < m) { prefetch(jn, b ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const uint32_t item = item_offset + (uint32_t)j;
+        double fv[EPT], yv[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = tid + e * T;
+            if (i < n) { fv[e] = fbuf[b * NP + i]; yv[e] = (double)ybuf[b * NP + i]; }
+            else { fv[e] = yv[e] = 0.0; }
+        }
+        double cv[2] = {beta[2 * j], beta[2 * j + 1]};
+        double pv[2] = {cv[0], cv[1]};
+        double cv_ll = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
+            pv[k] = __dadd_rn(cv[k], __dmul_rn(pstep[2 * j + k], z));                   // :22
+            const double pv_prior = dnorm_log(pv[k], pm[2 * j + k], psd[2 * j + k]);    // :25
+            const double cv_prior = dnorm_log(cv[k], pm[2 * j + k], psd[2 * j + k]);    // :26
+            double part_p = 0.0, part_c = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (yv[e] != 0.0) {
+                    part_p -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27
+                    if (k == 0) part_c -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
+                }
+            const double pv_ll = block_sum(part_p, red[2 * k]);
+            if (k == 0) cv_ll = block_sum(part_c, red[2 * k + 1]);
+            const double r = pv_prior + pv_ll - cv_prior - cv_ll;                       // :29
+            const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
+            if (log(u) < r) { cv[k] = pv[k]; cv_ll = pv_ll; } else pv[k] = cv[k];       // :30-35
+        }
+        if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
+        j = jn;
+        b ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta, const double* __restrict__ f, int64_t ld,
                                                       const int8_t* __restrict__ y8, int64_t ldy,
                                                       const double* __restrict__ theta, const double* __restrict__ pm,
@@ -710,15 +798,39 @@ __global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta,
     if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
 }
 
+#define BETA_PERSIST_CASE(E, MT)                                                                                             \
+    {                                                                                                                            \
+        const size_t smem = (size_t)2 * (E) * threads * 9;                                                                       \
+        int grid = 0;                                                                                                            \
+        GP_TRY(persistent_grid(k_beta_persist<E, MT>, threads, smem, m, &grid));                                                 \
+        if (grid > 0) {                                                                                                          \
+            GP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));                                                                  \
+            GP_LAUNCH((k_beta_persist<E, MT>), grid, threads, smem, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, m, key,  \
+                      item_offset, sp, work);                                                                                    \
+            launched = true;                                                                                                     \
+        }                                                                                                                        \
+    }
+
 int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, const int8_t* y8, int64_t ldy,
                 const double* theta, const double* pm, const double* psd, const double* pstep, int n, int m,
-                RngKey key, uint32_t item_offset, int* status) {
+                RngKey key, uint32_t item_offset, int* status, int* work) {
     (void)status;
     if (m <= 0) return GPIRT_B200_OK;
     int ept, threads;
     item_cta_shape(n, ept, threads);
     const double* sp = nullptr;
     GP_TRY(softplus_table(&sp));
+    if (work && ept && item_kernels_persistent()) {
+        bool launched = false;
+        switch (ept) {
+            case 1: BETA_PERSIST_CASE(1, 512) break;
+            case 2: BETA_PERSIST_CASE(2, 512) break;
+            case 4: if (threads > 512) BETA_PERSIST_CASE(4, 1024) else BETA_PERSIST_CASE(4, 512) break;
+            default: BETA_PERSIST_CASE(8, 512) break;
+        }
+        GP_CUDA(cudaGetLastError());
+        if (launched) return GPIRT_B200_OK;
+    }
     switch (ept) {
         case 1: GP_LAUNCH((k_beta<1, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
         case 2: GP_LAUNCH((k_beta<2, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;

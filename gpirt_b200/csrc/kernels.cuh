@@ -39,7 +39,7 @@ int launch_theta_draw(cudaStream_t st, const double* logPt, int64_t ld, const do
 // Metropolis step for the two mean coefficients of every item (draw-beta.cpp)
 int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, const int8_t* y8, int64_t ldy,
                 const double* theta, const double* pm, const double* psd, const double* pstep, int n, int m,
-                RngKey key, uint32_t item_offset, int* status);
+                RngKey key, uint32_t item_offset, int* status, int* work = nullptr);
 // out[j] = ll_bar(f_j, y_j, mu_j) for explicit mu (host-API helper)
 int launch_ll_bar(cudaStream_t st, const double* f, const double* y, const double* mu, int n, int m, double* out);
 // IRF = plogis(sum / S)

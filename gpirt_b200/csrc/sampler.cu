@@ -462,7 +462,7 @@ int gpirt_b200_sampler::step_draw_theta(uint32_t sweep) {
 // beta = draw_beta(beta, X, y, f, ...) with X.col(1) = the NEW theta                 gpirtMCMC.cpp:71-73, draw-beta.cpp
 int gpirt_b200_sampler::step_draw_beta(uint32_t sweep) {
     tic(GPIRT_B200_T_BETA);
-    GP_TRY(launch_beta(stream, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1));
+    GP_TRY(launch_beta(stream, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1, work + 1));
     toc();
     return GPIRT_B200_OK;
 }
@@ -501,7 +501,9 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         toc_on(sg, st_beta);
         GP_CUDA(cudaEventRecord(ev_z, st_beta));
         Seg sb = tic_on(GPIRT_B200_T_BETA, st_beta);
-        GP_TRY(launch_beta(st_beta, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1));
+        // one CTA per item here, not the persistent variant: its CTAs retire every few microseconds, so the chain's short
+        // high-priority kernels get SMs (a persistent CTA owns the whole register file of its SM: measured +0.5 ms/sweep)
+        GP_TRY(launch_beta(st_beta, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1, nullptr));
         toc_on(sb, st_beta);
         GP_CUDA(cudaEventRecord(ev_beta, st_beta));
     }
