@@ -144,6 +144,14 @@ int launch_rng_probe(cudaStream_t st, RngKey key, uint32_t purpose, uint32_t str
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ESS_ITER_CAP = 10000;
 
+// log-likelihood term of one cell, 0 for a missing cell (y = 0; the reference skips NA, log-likelihood.cpp:18,32).
+// Branch-free on purpose: with `if (y != 0)` around every term the compiler cannot interleave the independent
+// evaluations of a thread's values and the FP64 dependency chains run one after the other.
+__device__ __forceinline__ double obs_term(const double* __restrict__ sp, double y, double a) {
+    const double t = ll_term_fast(sp, a);
+    return (y != 0.0) ? t : 0.0;
+}
+
 template <int EPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
                       int64_t ldy, const double* __restrict__ theta, const double* __restrict__ beta, int n, RngKey key,
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const doub
     double part = 0.0;
 #pragma unroll
     for (int e = 0; e < EPT; ++e)
-        if (yv[e] != 0.0) part -= ll_term_fast(sp, yv[e] * (fv[e] + gm[e]));
+        part -= obs_term(sp, yv[e], yv[e] * (fv[e] + gm[e]));
     const double ll_cur = block_sum(part, red[0]);
     const double u = rng_uniform(key, P_ESS_U, item, 0u);
     const double log_y = ll_cur + log(u);                                            // draw-f.cpp:28-29
@@ -196,9 +204,9 @@ __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const doub
         part = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
-            if (yv[e] != 0.0) {
+            {
                 const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
-                part -= ll_term_fast(sp, yv[e] * (fp + gm[e]));
+                part -= obs_term(sp, yv[e], yv[e] * (fp + gm[e]));
             }
         const double ll_new = block_sum(part, red[iter & 1]);
         if (ll_new > log_y) break;                                                   // :45 strict
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(MAXT) k_ess_persist(double* __restrict__ f, co
         double part = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
-            if (yv[e] != 0.0) part -= ll_term_fast(sp, yv[e] * (fv[e] + gm[e]));
+            part -= obs_term(sp, yv[e], yv[e] * (fv[e] + gm[e]));
         const double ll_cur = block_sum(part, red[0]);
         const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));          // draw-f.cpp:28-29
         const double TWO_PI = 6.283185307179586476925286766559;
@@ -350,9 +358,9 @@ __global__ void __launch_bounds__(MAXT) k_ess_persist(double* __restrict__ f, co
             part = 0.0;
 #pragma unroll
             for (int e = 0; e < EPT; ++e)
-                if (yv[e] != 0.0) {
+                {
                     const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
-                    part -= ll_term_fast(sp, yv[e] * (fp + gm[e]));
+                    part -= obs_term(sp, yv[e], yv[e] * (fp + gm[e]));
                 }
             const double ll_new = block_sum(part, red[iter & 1]);
             if (ll_new > log_y) break;                                                   // :45 strict
@@ -680,9 +688,9 @@ __global__ void __launch_bounds__(MAXT) k_beta(double* __restrict__ beta, const 
         double part_p = 0.0, part_c = 0.0;
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
-            if (yv[e] != 0.0) {
-                part_p -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27  ll_bar(rho, y, X * pv)
-                if (k == 0) part_c -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
+            {
+                part_p -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27  ll_bar(rho, y, X * pv)
+                if (k == 0) part_c -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
             }
         const double pv_ll = block_sum(part_p, red[2 * k]);
         if (k == 0) cv_ll = block_sum(part_c, red[2 * k + 1]);
@@ -745,9 +753,9 @@ __global__ void __launch_bounds__(MAXT) k_beta_persist(double* __restrict__ beta
             double part_p = 0.0, part_c = 0.0;
 #pragma unroll
             for (int e = 0; e < EPT; ++e)
-                if (yv[e] != 0.0) {
-                    part_p -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27
-                    if (k == 0) part_c -= ll_term_fast(sp, yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
+                {
+                    part_p -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27
+                    if (k == 0) part_c -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
                 }
             const double pv_ll = block_sum(part_p, red[2 * k]);
             if (k == 0) cv_ll = block_sum(part_c, red[2 * k + 1]);
