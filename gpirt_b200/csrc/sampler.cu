@@ -83,6 +83,23 @@ struct gpirt_b200_sampler {
     bool solve_ready = false;    // kstar already holds S^-1 K* and s the predictive sd for the current theta (ev_solve)
     cudaEvent_t ev_linv = nullptr, ev_solve = nullptr;
     int fstar_solves(cudaStream_t st);
+    // solve_mode 1 (default with items sharded over GPUs): the two triangular solves for this rank's slice of the grid
+    // columns as blocked substitutions with the 128-block inverses of the factorisation — no L^-1.  The forward steps
+    // trail the Cholesky panels on st_trsm; only the backward pass (32 short steps) follows the factorisation.  With
+    // few right-hand sides per rank this replaces the replicated 1.3 ms L^-1 + products by a ~0.4 ms chain.
+    int solve_mode = 0;
+    cudaStream_t st_trsm = nullptr;
+    cudaEvent_t ev_trsm = nullptr;
+    bool local_solve_ready = false;   // this rank's slice of S^-1 K* and s is complete on st_trsm (ev_solve), not yet gathered
+    void grid_slice(int& c0, int& nc) const {
+        const int per = (int)ceil_div(N_GRID, comm.world);
+        c0 = std::min(N_GRID, comm.rank * per);
+        nc = std::min(N_GRID, c0 + per) - c0;
+    }
+    int trsm_kstar(cudaStream_t st);
+    int trsm_fwd_step(cudaStream_t st, int k);
+    int trsm_bwd(cudaStream_t st);
+    int gather_solves(cudaStream_t st);
     bool has_missing = false;
     bool timing = true;
     uint32_t sweep_counter = 0;
@@ -206,7 +223,11 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_CUDA(cudaStreamCreateWithPriority(&lookahead.aux, cudaStreamNonBlocking, greatest));
         GP_CUDA(cudaStreamCreateWithPriority(&st_beta, cudaStreamNonBlocking, least));
         GP_CUDA(cudaStreamCreateWithPriority(&st_lz, cudaStreamNonBlocking, least));
-        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        GP_CUDA(cudaStreamCreateWithPriority(&st_trsm, cudaStreamNonBlocking, greatest));
+        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_trsm}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        const char* sm = getenv("GPIRT_SOLVE_MODE");
+        solve_mode = sm ? atoi(sm) : (comm.world > 1 ? 1 : 0);
+        if (opts.fstar_mode != 0) solve_mode = 0;   // the literal per-item form needs L^-1
         const char* pe = getenv("GPIRT_PIPELINE");
         if (pe) pipeline = atoi(pe) != 0;
     }
@@ -266,7 +287,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
             GP_TRY(dp_L.init(stream, n, n, 128));
             GP_TRY(dp_A.init(stream, N_GRID, n, 128));
             GP_TRY(dp_B.init(stream, m, n, 64));
-            if (opts.fstar_mode == 0) {
+            if (opts.fstar_mode == 0 && solve_mode == 0) {
                 const int per = (int)ceil_div(N_GRID, comm.world), c0 = min(N_GRID, comm.rank * per), nc = min(N_GRID, c0 + per) - c0;
                 GP_TRY(dp_Linv.init(stream, n, n, 128));
                 GP_TRY(dp_LinvT.init(stream, n, n, 128));
@@ -288,6 +309,7 @@ int gpirt_b200_sampler::check_status() {
     GP_CUDA(cudaStreamSynchronize(stream));
     if (st_lz) GP_CUDA(cudaStreamSynchronize(st_lz));       // side streams may still run the next sweep's K* solves
     if (st_beta) GP_CUDA(cudaStreamSynchronize(st_beta));
+    if (st_trsm) GP_CUDA(cudaStreamSynchronize(st_trsm));
     flush_timers();
     if (h[0]) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
     if (h[1]) { set_last_error("elliptical slice sampler did not terminate (NaN log-likelihood?)"); return GPIRT_B200_ERR_ESS; }
@@ -302,9 +324,11 @@ int gpirt_b200_sampler::step_rebuild() {
     tic(GPIRT_B200_T_CHOL);
     GP_TRY(potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, &lookahead));
     toc();
-    tic(GPIRT_B200_T_TRTRI);   // L^-1 once per sweep: every triangular solve of draw_fstar becomes a triangular GEMM
-    GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
-    toc();
+    if (solve_mode == 0) {
+        tic(GPIRT_B200_T_TRTRI);   // L^-1 once per sweep: every triangular solve of draw_fstar becomes a triangular GEMM
+        GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
+        toc();
+    }
     return GPIRT_B200_OK;
 }
 
@@ -346,8 +370,66 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
 // The item-independent part of draw_fstar (draw-fstar.cpp:17-20): kstar = K(theta, theta*), tmp = L^-1 kstar,
 // s = 1 - sqrt(colsum(tmp % tmp)), and A = L^-T tmp so that K*^T L^-T L^-1 f_j = A^T f_j needs one product per sweep
 // instead of two solves per item.  Depends on theta and L only, so the pipelined sweep runs it beside the ESS.
+int gpirt_b200_sampler::trsm_kstar(cudaStream_t st) {   // K(theta, theta*) for this rank's grid columns      :17
+    int c0, nc;
+    grid_slice(c0, nc);
+    if (nc > 0) GP_TRY(launch_se_cov(st, theta, n, theta_star + c0, nc, 0.0, false, kstar + (int64_t)c0 * ldn, ldn));
+    return GPIRT_B200_OK;
+}
+// forward substitution, block row k:  X_k = L_kk^-1 B_k,  B[below] -= L[below, k] X_k   (B = kstar, X = kstar2)     :19
+int gpirt_b200_sampler::trsm_fwd_step(cudaStream_t st, int k) {
+    int c0, nc;
+    grid_slice(c0, nc);
+    if (nc <= 0) return GPIRT_B200_OK;
+    const int r0 = k * CHOL_NB, nb = std::min(CHOL_NB, n - r0), rem = n - r0 - nb;
+    double* B = kstar + (int64_t)c0 * ldn;
+    double* X = kstar2 + (int64_t)c0 * ldn;
+    GP_TRY(gemm_f64(st, false, false, G(nb, nc, nb, Dinv + r0, ldn, B + r0, ldn, X + r0, ldn, 1.0, 0.0, TRI_A_LOWER)));
+    if (rem > 0)
+        GP_TRY(gemm_f64(st, false, false, G(rem, nc, nb, L + (r0 + nb) + (int64_t)r0 * ldn, ldn, X + r0, ldn, B + r0 + nb, ldn, -1.0, 1.0, TRI_NONE)));
+    return GPIRT_B200_OK;
+}
+// s from tmp = L^-1 K* (:20), then the backward substitution  L^T A = tmp  (tmp = kstar2 is consumed, A -> kstar)    :24
+int gpirt_b200_sampler::trsm_bwd(cudaStream_t st) {
+    int c0, nc;
+    grid_slice(c0, nc);
+    if (nc <= 0) return GPIRT_B200_OK;
+    double* A = kstar + (int64_t)c0 * ldn;
+    double* Y = kstar2 + (int64_t)c0 * ldn;
+    GP_TRY(launch_fstar_sd(st, Y, ldn, n, nc, s + c0));
+    const int nblk = (int)ceil_div(n, CHOL_NB);
+    for (int k = nblk - 1; k >= 0; --k) {
+        const int r0 = k * CHOL_NB, nb = std::min(CHOL_NB, n - r0);
+        GP_TRY(gemm_f64(st, true, false, G(nb, nc, nb, Dinv + r0, ldn, Y + r0, ldn, A + r0, ldn, 1.0, 0.0, TRI_A_UPPER)));
+        if (r0 > 0)
+            GP_TRY(gemm_f64(st, true, false, G(r0, nc, nb, L + r0, ldn, A + r0, ldn, Y, ldn, -1.0, 1.0, TRI_NONE)));
+    }
+    return GPIRT_B200_OK;
+}
+int gpirt_b200_sampler::gather_solves(cudaStream_t st) {
+    if (comm.world > 1) {
+        const int per = (int)ceil_div(N_GRID, comm.world);
+        GP_TRY(comm_allgather_f64(comm, kstar, (size_t)per * ldn, st));
+        GP_TRY(comm_allgather_f64(comm, s, (size_t)per, st));
+    }
+    if (use_i8gemm) GP_TRY(dp_A.slice_kcontig(st, kstar, ldn));   // row k of A^T = column k of S^-1 K*
+    return GPIRT_B200_OK;
+}
+
 int gpirt_b200_sampler::fstar_solves(cudaStream_t st) {
     const int N = N_GRID;
+    if (solve_mode == 1) {
+        Seg a = tic_on(GPIRT_B200_T_KSTAR, st);
+        GP_TRY(trsm_kstar(st));
+        toc_on(a, st);
+        Seg b = tic_on(GPIRT_B200_T_TRSM, st);
+        const int nblk = (int)ceil_div(n, CHOL_NB);
+        for (int k = 0; k < nblk; ++k) GP_TRY(trsm_fwd_step(st, k));
+        GP_TRY(trsm_bwd(st));
+        GP_TRY(gather_solves(st));
+        toc_on(b, st);
+        return GPIRT_B200_OK;
+    }
     // with items sharded over GPUs this part would be replicated: instead every rank solves for its slice of the 1001
     // grid columns and the slices are all-gathered (n x 1001 doubles) — the caller passes the main stream then
     const int per = (int)ceil_div(N, comm.world), c0 = min(N, comm.rank * per), nc = min(N, c0 + per) - c0;
@@ -386,8 +468,14 @@ int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
     const int N = N_GRID;
     if (opts.fstar_mode == 0) {
         if (solve_ready) GP_CUDA(cudaStreamWaitEvent(stream, ev_solve, 0));   // done under the previous sweep's tail / this sweep's ESS
-        else GP_TRY(fstar_solves(stream));
+        else if (local_solve_ready) {   // this rank's slice was solved behind the factorisation: gather it now
+            GP_CUDA(cudaStreamWaitEvent(stream, ev_solve, 0));
+            tic(GPIRT_B200_T_TRSM);
+            GP_TRY(gather_solves(stream));
+            toc();
+        } else GP_TRY(fstar_solves(stream));
         solve_ready = false;
+        local_solve_ready = false;
         tic(GPIRT_B200_T_FSTAR_GEMM);
         if (use_i8gemm) {
             GP_TRY(dp_B.slice_kcontig(stream, f, ldn));
@@ -398,6 +486,7 @@ int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
         toc();
     } else {
         solve_ready = false;
+        local_solve_ready = false;
         tic(GPIRT_B200_T_KSTAR);
         GP_TRY(launch_se_cov(stream, theta, n, theta_star, N, 0.0, false, kstar, ldn));          // :17
         toc();
@@ -510,8 +599,21 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     tic(GPIRT_B200_T_KBUILD);
     GP_TRY(launch_se_cov(stream, theta, n, theta, n, 0.001, true, L, ldn));
     toc();
+    const bool trsm_route = solve_mode == 1 && opts.fstar_mode == 0;
+    if (trsm_route) {   // K* for this rank's grid columns as soon as theta is known
+        GP_CUDA(cudaStreamWaitEvent(st_trsm, ev_theta, 0));
+        Seg a = tic_on(GPIRT_B200_T_KSTAR, st_trsm);
+        GP_TRY(trsm_kstar(st_trsm));
+        toc_on(a, st_trsm);
+    }
     bool first = true;
     lookahead.after_panel = [&](int k, int nblk, cudaEvent_t done) -> int {
+        if (trsm_route) {   // forward substitution step k trails panel k
+            GP_CUDA(cudaStreamWaitEvent(st_trsm, done, 0));
+            Seg sg = tic_on(GPIRT_B200_T_TRSM, st_trsm);
+            GP_TRY(trsm_fwd_step(st_trsm, k));
+            toc_on(sg, st_trsm);
+        }
         if ((k + 1) % lz_group != 0 && k != nblk - 1) return GPIRT_B200_OK;
         const int g = k / lz_group;
         const int r0 = g * lz_group * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
@@ -545,14 +647,22 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     lookahead.after_panel = nullptr;
     GP_TRY(rc);
     toc();
-    tic(GPIRT_B200_T_TRTRI);
-    GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
-    toc();
+    if (!trsm_route) {
+        tic(GPIRT_B200_T_TRTRI);
+        GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
+        toc();
+    } else {   // backward substitution behind the last forward step; the next sweep's ESS does not wait for it
+        Seg sg = tic_on(GPIRT_B200_T_TRSM, st_trsm);
+        GP_TRY(trsm_bwd(st_trsm));
+        toc_on(sg, st_trsm);
+        GP_CUDA(cudaEventRecord(ev_solve, st_trsm));
+        local_solve_ready = true;
+    }
     GP_CUDA(cudaStreamWaitEvent(stream, ev_lz, 0));
     GP_CUDA(cudaStreamWaitEvent(stream, ev_beta, 0));
     nu_ready = true;
     nu_sweep = next_sweep;
-    if (opts.fstar_mode == 0 && comm.world <= 1) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
+    if (opts.fstar_mode == 0 && comm.world <= 1 && !trsm_route) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
         GP_CUDA(cudaEventRecord(ev_linv, stream));
         GP_CUDA(cudaStreamWaitEvent(st_solve, ev_linv, 0));
         GP_TRY(fstar_solves(st_solve));
@@ -585,8 +695,8 @@ void gpirt_b200_sampler::destroy() {
     for (auto e : lookahead.ev_bulk) cudaEventDestroy(e);
     lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
-    for (cudaStream_t* q : {&st_beta, &st_lz}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
-    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaStream_t* q : {&st_beta, &st_lz, &st_trsm}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
+    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_trsm}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
     dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
@@ -746,7 +856,7 @@ int gpirt_b200_sampler_sweep(gpirt_b200_sampler* s, int n_sweeps, int accumulate
 int gpirt_b200_sampler_step(gpirt_b200_sampler* s, int step, uint32_t sweep) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->nu_ready = false;
-    if (s->solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = false; }
+    if (s->solve_ready || s->local_solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = s->local_solve_ready = false; }
     int rc;
     switch (step) {
         case GPIRT_B200_STEP_DRAW_F: rc = s->step_draw_f(sweep); break;
@@ -810,7 +920,7 @@ int gpirt_b200_sampler_set(gpirt_b200_sampler* s, int field, const double* host_
     double* dev; int64_t ld; int rows, cols;
     if (field_shape(s, field, &dev, &ld, &rows, &cols)) return GPIRT_B200_ERR_ARG;
     s->nu_ready = false;
-    if (s->solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = false; }
+    if (s->solve_ready || s->local_solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = s->local_solve_ready = false; }
     GP_TRY(upload_padded(dev, ld, host_in, rows, cols, s->stream));
     GP_CUDA(cudaStreamSynchronize(s->stream));
     return GPIRT_B200_OK;
@@ -836,7 +946,7 @@ int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->pipeline = enabled != 0;
     s->nu_ready = false;
-    if (s->solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = false; }
+    if (s->solve_ready || s->local_solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = s->local_solve_ready = false; }
     return GPIRT_B200_OK;
 }
 

@@ -351,6 +351,31 @@ def test_chain_fixed_point_products_match_dmma_products(G, monkeypatch):
     assert np.max(np.abs(a["IRFs"] - b["IRFs"])) <= 1e-9
 
 
+@pytest.mark.parametrize("n,m", [(100, 40), (400, 150), (700, 320)])
+def test_chain_blocked_substitution_solves_match_inverse_route(G, O, n, m, monkeypatch):
+    """GPIRT_SOLVE_MODE=1 (the default when items are sharded over GPUs): L^-1 K* and L^-T(.) by blocked substitution
+    with the 128-block inverses, forward steps trailing the Cholesky panels, instead of L^-1 + triangular products
+    (draw-fstar.cpp:19,24).  Same chain as the inverse route, and in lock-step with the oracle."""
+    from gpirt_b200 import ResponseMatrix
+    prob = make_problem(n, m, seed=n + 5, missing=0.04)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GPIRT_SOLVE_MODE", flag)
+        out[flag] = G.gpirtMCMC(ResponseMatrix(prob["y"]), 3, 1, beta_prior_means=prob["pm"], beta_prior_sds=prob["psd"],
+                                beta_proposal_sds=prob["pstep"], theta_init=prob["theta"], seed=31)
+    a, b = out["1"], out["0"]
+    assert np.array_equal(a["theta"], b["theta"])
+    assert np.max(np.abs(a["beta"] - b["beta"])) <= 1e-10
+    assert np.max(np.abs(a["f"] - b["f"])) <= 1e-8
+    assert np.max(np.abs(a["IRFs"] - b["IRFs"])) <= 1e-8
+    if n <= 400:
+        rng = O.Rng.keyed(31)
+        want = O.mcmc(prob["y"], prob["theta"], 3, 1, prob["pm"], prob["psd"], prob["pstep"], rng, theta_cdf_mode=1)
+        assert np.array_equal(a["theta"], want["theta"])
+        assert np.max(np.abs(a["f"] - want["f"])) <= 1e-7
+        assert np.max(np.abs(a["IRFs"] - want["IRFs"])) <= 1e-7
+
+
 def test_senate116_short_chain(G, O):
     import warnings
     import gpirt_b200
