@@ -38,6 +38,16 @@ __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_
 int pool_alloc(void** p, size_t bytes, cudaStream_t st);
 void pool_free(void* p, cudaStream_t st);
 
+// Function attributes (dynamic shared memory limits) are per device: `flags` is a function-local static array; returns
+// true the first time the calling code runs on the current device.
+inline bool first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
 // launch counter (gpu_launches in bench.py): every kernel launch in this library goes through GP_LAUNCH
 extern int64_t g_launch_count;
 #define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \

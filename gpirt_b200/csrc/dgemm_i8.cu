@@ -457,13 +457,12 @@ int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double
         return GPIRT_B200_ERR_ARG;
     }
     static int n_sm = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
         int dev = 0;
         GP_CUDA(cudaGetDevice(&dev));
         GP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         GP_CUDA(cudaFuncSetAttribute(k_dgemm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
-        attr_set = true;
     }
     TileSched sched;
     sched.mtiles = (int)(A.rows_pad / DG_BM);

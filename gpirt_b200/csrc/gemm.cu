@@ -7,12 +7,10 @@ namespace gpirt {
 template <int BM, int BN, int WM, int WN, bool TA, bool TB, bool BABS>
 static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
     auto kern = gemm_f64_kernel<BM, BN, WM, WN, TA, TB, BABS>;
-    static bool configured = false;  // per instantiation
+    static bool configured[64] = {false};  // per instantiation and device
     constexpr size_t smem = gemm_smem_bytes<BM, BN>();
-    if (!configured) {
+    if (first_use_on_device(configured))
         GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     dim3 grid((unsigned)(ceil_div(g.N, BN) * ceil_div(g.M, BM)), 1, (unsigned)g.batch);
     GP_LAUNCH(kern, grid, dim3(WM * WN * 32), smem, stream, g);
     GP_CUDA(cudaGetLastError());

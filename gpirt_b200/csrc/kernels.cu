@@ -544,6 +544,7 @@ __global__ void __launch_bounds__(128) k_theta_prep(const double* __restrict__ f
     if (k >= N) return;
     const int per = (int)ceil_div(m, n_chunks), j0 = chunk * per, j1 = min(m, j0 + per);
     double acc = 0.0;
+#pragma unroll 4   // four independent evaluations in flight; the sum keeps its order
     for (int j = j0; j < j1; ++j) {
         const double v = fstar[k + (int64_t)j * ld];
         const double a = fabs(v);

@@ -95,11 +95,9 @@ __global__ void __launch_bounds__(256, 1) k_potrf_trtri(double* __restrict__ A, 
 static int launch_diag(cudaStream_t stream, double* A, int64_t lda, int n_total, double* Dinv, int64_t ldd, int* d_status,
                        int do_factor) {
     constexpr size_t smem = (size_t)(2 * DIAG_NB * (DIAG_NB + 1) + DIAG_NB) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured))
         GP_CUDA(cudaFuncSetAttribute(k_potrf_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     GP_LAUNCH(k_potrf_trtri, (unsigned)ceil_div(n_total, DIAG_NB), 256, smem, stream, A, lda, n_total, Dinv, ldd, d_status,
               do_factor);
     GP_CUDA(cudaGetLastError());
@@ -454,11 +452,9 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
                    CholLookahead* la) {
     if (n <= 0) return GPIRT_B200_OK;
     constexpr size_t smem = (size_t)(DB * DLD + 3 * DB) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (first_use_on_device(configured))
         GP_CUDA(cudaFuncSetAttribute(k_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     const int nblk = (int)ceil_div(n, CHOL_NB);
     const bool two = la && la->aux && nblk > 2;
     if (two) {
