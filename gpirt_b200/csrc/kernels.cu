@@ -107,6 +107,49 @@ int launch_fill_normal(cudaStream_t st, double* Z, int n, int m, int64_t ld, Rng
     return GPIRT_B200_OK;
 }
 
+// The same normals written straight as the 8 balanced base-128 digit planes of the fixed-point product nu = L Z
+// (dgemm_i8.cu): |z| < 8.7 for every 53-bit Box-Muller draw, so all columns share the scale 2^4 and no column-maximum
+// pass (and no FP64 copy of Z) is needed.  One thread = 4 consecutive respondents = one 32-bit store per plane.
+constexpr int Z_FIXED_EXP = 4;
+__global__ void __launch_bounds__(256) k_fill_normal_planes(int8_t* __restrict__ planes, double* __restrict__ scale,
+                                                            int64_t rows_pad, int64_t k_pad, int n, RngKey key,
+                                                            uint32_t purpose, uint32_t item_offset,
+                                                            double* __restrict__ Z, int64_t ld) {
+    const int quad = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int i0 = 4 * quad;
+    if (quad == 0) scale[j] = 0.25;                 // 2^(Z_FIXED_EXP - 6)
+    if (i0 >= n) return;
+    double z[4];
+    rng_normal_pair(key, purpose, item_offset + (uint32_t)j, (uint32_t)(2 * quad), z[0], z[1]);
+    if (i0 + 2 < n) rng_normal_pair(key, purpose, item_offset + (uint32_t)j, (uint32_t)(2 * quad + 1), z[2], z[3]);
+    else z[2] = z[3] = 0.0;
+    unsigned packed[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double v = (i0 + b < n) ? z[b] : 0.0;
+        if (Z && i0 + b < n) Z[i0 + b + (int64_t)j * ld] = v;
+        long long X = __double2ll_rn(v * 2251799813685248.0);   // 2^(55 - Z_FIXED_EXP) = 2^51
+#pragma unroll
+        for (int s = 7; s >= 1; --s) {
+            const int d = (int)((X + 64) & 127) - 64;
+            packed[s] |= (unsigned)(d & 0xFF) << (8 * b);
+            X = (X - d) >> 7;
+        }
+        packed[0] |= (unsigned)((int)X & 0xFF) << (8 * b);
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+        *reinterpret_cast<unsigned*>(planes + ((int64_t)s * rows_pad + j) * k_pad + i0) = packed[s];
+}
+int launch_fill_normal_planes(cudaStream_t st, int8_t* planes, double* scale, int64_t rows_pad, int64_t k_pad, int n, int m,
+                              RngKey key, uint32_t purpose, uint32_t item_offset, double* Z_or_null, int64_t ld) {
+    if (n <= 0 || m <= 0) return GPIRT_B200_OK;
+    dim3 grid((unsigned)ceil_div(ceil_div(n, 4), 256), (unsigned)m);
+    GP_LAUNCH(k_fill_normal_planes, grid, 256, 0, st, planes, scale, rows_pad, k_pad, n, key, purpose, item_offset, Z_or_null, ld);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
 __global__ void k_init_beta(double* beta, const double* pm, const double* psd, int m, RngKey key, uint32_t item_offset) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;

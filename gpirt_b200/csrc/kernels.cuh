@@ -17,6 +17,10 @@ int launch_ingest_y(cudaStream_t st, const double* y, int n, int m, int8_t* y8, 
 // Z[i,j] = standard normal addressed (sweep, purpose, item_offset + j, i)
 int launch_fill_normal(cudaStream_t st, double* Z, int n, int m, int64_t ld, RngKey key, uint32_t purpose,
                        uint32_t item_offset);
+// the same normals as int8 digit planes (operand of the fixed-point L Z product) with the fixed column scale 2^-2;
+// Z_or_null: also store them as doubles
+int launch_fill_normal_planes(cudaStream_t st, int8_t* planes, double* scale, int64_t rows_pad, int64_t k_pad, int n, int m,
+                              RngKey key, uint32_t purpose, uint32_t item_offset, double* Z_or_null, int64_t ld);
 // beta[p,j] = pm + psd * z  (gpirtMCMC.cpp:23-27)
 int launch_init_beta(cudaStream_t st, double* beta, const double* pm, const double* psd, int m, RngKey key,
                      uint32_t item_offset);

@@ -349,12 +349,14 @@ static GemmArgs G(int M, int N, int K, const double* A, int64_t lda, const doubl
 int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
     const RngKey k = key_at(sweep);
     tic(GPIRT_B200_T_FILL_Z);
-    GP_TRY(launch_fill_normal(stream, Z, n, m, ldn, k, sweep == 0 ? P_INIT_F_Z : P_ESS_Z, item_offset));
+    if (use_i8gemm)   // the normals go straight into the digit planes of the product's operand
+        GP_TRY(launch_fill_normal_planes(stream, dp_B.planes, dp_B.scale, dp_B.rows_pad, dp_B.k_pad, n, m, k,
+                                         sweep == 0 ? P_INIT_F_Z : P_ESS_Z, item_offset, nullptr, ldn));
+    else GP_TRY(launch_fill_normal(stream, Z, n, m, ldn, k, sweep == 0 ? P_INIT_F_Z : P_ESS_Z, item_offset));
     toc();
     tic(GPIRT_B200_T_LZ_GEMM);   // nu_j = cholS z_j for all items in one product (mvnormal.h:10)
     if (use_i8gemm) {
         GP_TRY(dp_L.slice_mcontig(stream, L, ldn, true, 0, n, L_FIXED_EXP));
-        GP_TRY(dp_B.slice_kcontig(stream, Z, ldn));
         GP_TRY(dgemm_i8(stream, dp_L, dp_B, sweep == 0 ? f : nu, ldn, DG_TRI_LOWER, 0, n, false, LZ_GROUP_COLS));
     } else {
         GP_TRY(gemm_f64(stream, false, false, G(n, m, n, L, ldn, Z, ldn, sweep == 0 ? f : nu, ldn, 1.0, 0.0, TRI_A_LOWER)));
@@ -586,7 +588,10 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     GP_CUDA(cudaStreamWaitEvent(st_beta, ev_theta, 0));
     {
         Seg sg = tic_on(GPIRT_B200_T_FILL_Z, st_beta);
-        GP_TRY(launch_fill_normal(st_beta, Z, n, m, ldn, key_at(next_sweep), P_ESS_Z, item_offset));
+        if (use_i8gemm)
+            GP_TRY(launch_fill_normal_planes(st_beta, dp_B.planes, dp_B.scale, dp_B.rows_pad, dp_B.k_pad, n, m, key_at(next_sweep),
+                                             P_ESS_Z, item_offset, nullptr, ldn));
+        else GP_TRY(launch_fill_normal(st_beta, Z, n, m, ldn, key_at(next_sweep), P_ESS_Z, item_offset));
         toc_on(sg, st_beta);
         GP_CUDA(cudaEventRecord(ev_z, st_beta));
         Seg sb = tic_on(GPIRT_B200_T_BETA, st_beta);
@@ -619,11 +624,6 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         const int r0 = g * lz_group * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
         if (first) {
             GP_CUDA(cudaStreamWaitEvent(st_lz, ev_z, 0));
-            if (use_i8gemm) {
-                Seg sz = tic_on(GPIRT_B200_T_LZ_GEMM, st_lz);
-                GP_TRY(dp_B.slice_kcontig(st_lz, Z, ldn));
-                toc_on(sz, st_lz);
-            }
             first = false;
         }
         GP_CUDA(cudaStreamWaitEvent(st_lz, done, 0));
