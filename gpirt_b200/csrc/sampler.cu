@@ -113,7 +113,7 @@ struct gpirt_b200_sampler {
     int* work = nullptr;   // item counters of the persistent per-item kernels: [0] ESS, [1] beta
     int *nprop = nullptr, *theta_idx = nullptr, *status = nullptr;  // status[0] chol, [1] ess, [2] theta-degenerate count
     unsigned long long* counters = nullptr;                        // [0] missing cells, [1] illegal cells
-    static constexpr int N_CHUNKS = 32;
+    static constexpr int N_CHUNKS = 128;   // item chunks of the D row sums: enough CTAs to cover the HBM latency of the column walk
 
     // ---- timers ----
     struct Seg { int timer; cudaEvent_t a, b; };
