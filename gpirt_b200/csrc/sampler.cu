@@ -89,7 +89,6 @@ struct gpirt_b200_sampler {
     // few right-hand sides per rank this replaces the replicated 1.3 ms L^-1 + products by a ~0.4 ms chain.
     int solve_mode = 0;
     cudaStream_t st_trsm = nullptr;
-    cudaEvent_t ev_trsm = nullptr;
     bool local_solve_ready = false;   // this rank's slice of S^-1 K* and s is complete on st_trsm (ev_solve), not yet gathered
     void grid_slice(int& c0, int& nc) const {
         const int per = (int)ceil_div(N_GRID, comm.world);
@@ -224,7 +223,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_CUDA(cudaStreamCreateWithPriority(&st_beta, cudaStreamNonBlocking, least));
         GP_CUDA(cudaStreamCreateWithPriority(&st_lz, cudaStreamNonBlocking, least));
         GP_CUDA(cudaStreamCreateWithPriority(&st_trsm, cudaStreamNonBlocking, greatest));
-        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_trsm}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         const char* sm = getenv("GPIRT_SOLVE_MODE");
         solve_mode = sm ? atoi(sm) : (comm.world > 1 ? 1 : 0);
         if (opts.fstar_mode != 0) solve_mode = 0;   // the literal per-item form needs L^-1
@@ -696,7 +695,7 @@ void gpirt_b200_sampler::destroy() {
     lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
     for (cudaStream_t* q : {&st_beta, &st_lz, &st_trsm}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
-    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_trsm}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
     dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
