@@ -395,6 +395,10 @@ def main():
                                  "estimator": "Geyer initial positive sequence per respondent; seconds = wall time of the "
                                               "gpirtMCMC(S, B, store_f=False) call incl. burn-in",
                                  "corr_with_generating_theta": float(abs(np.corrcoef(ch["theta"][1:].mean(axis=0), data["theta_true"])[0, 1]))}
+            if "e2e" in line:   # the same public call without the n x m x (S+1) f array: what bounds `e2e` is storing f
+                line["e2e"]["without_f_draws"] = {"value": (S_ess + B_ess) / el_ess, "unit": "sweeps/s",
+                                                  "note": "gpirtMCMC(%d, %d, store_f=False) wall time: theta, beta and IRFs "
+                                                          "still come back to the host every sweep" % (S_ess, B_ess)}
         except Exception as ex:
             line["theta_ess"] = {"error": repr(ex)}
 
