@@ -452,7 +452,7 @@ int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double
              int k_hi, bool accumulate, int group_cols, bool persistent) {
     if (A.rows <= 0 || B.rows <= 0) return GPIRT_B200_OK;
     if (!A.map || !B.map || A.k_pad != B.k_pad || A.box_rows != DG_BM || B.box_rows != DG_BN || k_lo % DG_KB != 0 || k_lo < 0 ||
-        k_hi > A.k || k_hi > B.k || A.k > 65536) {
+        k_hi > A.k || k_hi > B.k || A.k >= 65536) {
         set_last_error("dgemm_i8: operands do not match");
         return GPIRT_B200_ERR_ARG;
     }

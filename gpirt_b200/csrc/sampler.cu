@@ -281,7 +281,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     {   // GPIRT_GEMM_INT8 = 1 / 0 forces the fixed-point tensor-core products on / off (FP64 DMMA instead)
         const char* e = getenv("GPIRT_GEMM_INT8");
         use_i8gemm = e ? atoi(e) != 0 : (n >= 512 && std::max<int64_t>(m, opts.m_global) >= 256);   // same path on every shard
-        if (n > 65536) use_i8gemm = false;   // int32 accumulators hold 8 x 64 x 64 x K
+        if (n >= 65536) use_i8gemm = false;   // int32 accumulators hold 8 x 64 x 64 x K
         if (use_i8gemm) {
             GP_TRY(dp_L.init(stream, n, n, 128));
             GP_TRY(dp_A.init(stream, N_GRID, n, 128));
