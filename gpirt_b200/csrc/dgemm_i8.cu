@@ -8,7 +8,7 @@
 // so that
 //     sum_k a[i,k] b[j,k] = 2^(ea_i - 6) 2^(eb_j - 6) sum_{l} 128^-l  sum_{s+t=l} ( sum_k da_s[i,k] db_t[j,k] )
 // The innermost sums are int8 x int8 -> int32 tensor-core products and are EXACT (|.| <= (l+1) K 64^2 < 2^31 for
-// K <= 65536).  Levels l = 0..7 are kept (36 plane pairs); the dropped levels l >= 8 contribute less than
+// K < 65536).  Levels l = 0..7 are kept (36 plane pairs); the dropped levels l >= 8 contribute less than
 // 2^-53 2^(ea+eb) <= 2^-51 amax_i bmax_j per term of the dot product, i.e. the result carries an absolute error of at most
 // K 2^-51 amax_i bmax_j — the same order as the K 2^-53 sum|a||b| bound of an FP64 dot product when rows are not badly
 // scaled, which is the case for L (rows of unit norm), Z (normal draws), S^-1 K* and f.
