@@ -11,7 +11,7 @@ N_GRID = 1001
 
 # every symbol include/gpirt_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
-    "gpirt_b200_mcmc", "gpirt_b200_strerror", "gpirt_b200_last_error", "gpirt_b200_device_count",
+    "gpirt_b200_mcmc", "gpirt_b200_strerror", "gpirt_b200_last_error", "gpirt_b200_last_degenerate_theta", "gpirt_b200_device_count",
     "gpirt_b200_release_memory",
     "gpirt_b200_nccl_unique_id", "gpirt_b200_sampler_create", "gpirt_b200_sampler_init_draws",
     "gpirt_b200_sampler_sweep", "gpirt_b200_sampler_step", "gpirt_b200_sampler_get", "gpirt_b200_sampler_set",
@@ -38,7 +38,8 @@ class GpirtError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("device", C.c_int32), ("fstar_mode", C.c_int32), ("skip_f_draws", C.c_int32),
                 ("use_graph", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("m_global", C.c_int64),
-                ("item_offset", C.c_int64), ("nccl_unique_id", C.c_void_p)]
+                ("item_offset", C.c_int64), ("nccl_unique_id", C.c_void_p), ("thin", C.c_int32), ("reserved0", C.c_int32),
+                ("f_mean_out", C.POINTER(C.c_double)), ("f_sd_out", C.POINTER(C.c_double))]
 
 
 PROGRESS_CB = C.CFUNCTYPE(C.c_int, C.c_double, C.c_void_p)
@@ -60,6 +61,7 @@ def load():
     L = C.CDLL(LIB_PATH)
     L.gpirt_b200_strerror.restype = C.c_char_p
     L.gpirt_b200_last_error.restype = C.c_char_p
+    L.gpirt_b200_last_degenerate_theta.restype = C.c_int64
     L.gpirt_b200_mcmc.argtypes = [_dp, C.c_int64, C.c_int64, _dp, C.c_int, C.c_int, _dp, _dp, _dp, C.POINTER(Opts), _dp,
                                   _dp, _dp, _dp, PROGRESS_CB, C.c_void_p]
     L.gpirt_b200_nccl_unique_id.argtypes = [C.c_void_p]

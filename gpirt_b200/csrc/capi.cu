@@ -102,6 +102,7 @@ int gpirt_b200_chol_lower(double* S, int64_t n) {
     GP_TRY(a.alloc(ld * n)); GP_TRY(dinv.alloc(ld * CHOL_NB)); GP_TRY(flag.alloc(1));
     int* st = reinterpret_cast<int*>(flag.p);
     GP_CUDA(cudaMemset(st, 0, sizeof(double)));
+    GP_CUDA(cudaMemset(dinv.p, 0, (size_t)ld * CHOL_NB * sizeof(double)));   // potrf_lower_rl writes the lower triangles only
     GP_TRY(h2d(a.p, ld, S, n, n, n));
     int rc = potrf_lower_rl(0, a.p, ld, (int)n, dinv.p, ld, st);
     int h = 0;

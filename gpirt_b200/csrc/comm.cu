@@ -2,6 +2,7 @@
 
 #include <dlfcn.h>
 #include <cstring>
+#include <mutex>
 
 namespace gpirt {
 
@@ -38,7 +39,11 @@ int load_api() {
             if (!api.get_uid || !api.init_rank || !api.allreduce || !api.allgather || !api.destroy) { dlclose(api.handle); api.handle = nullptr; }
         }
     }
-    if (!api.handle) { set_last_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror()); return GPIRT_B200_ERR_NCCL; }
+    if (!api.handle) {
+        const char* why = dlerror();   // NULL when the library opened but a symbol was missing
+        set_last_error("NCCL (libnccl.so.2) could not be loaded: %s", why ? why : "a required entry point is missing");
+        return GPIRT_B200_ERR_NCCL;
+    }
     return GPIRT_B200_OK;
 }
 
@@ -60,22 +65,33 @@ int comm_unique_id(void* out128) {
 // The communicator outlives the sampler: ncclCommInitRank costs 0.3-3 s, far more than a short MCMC call.  A call that
 // passes a unique id creates (and caches) a communicator; a call with world_size > 1 and NO id re-uses the cached one
 // (same rank / world).  All ranks must take the same decision, as with any collective set-up.
-static struct { void* comm = nullptr; int rank = -1, world = 0; } g_cached;
+// `users` counts the live samplers that hold the cached pointer: it is never destroyed under them.
+static struct { void* comm = nullptr; int rank = -1, world = 0, users = 0; } g_cached;
+static std::mutex g_comm_mu;
 
 int comm_init(Comm& c, int rank, int world, const void* unique_id128) {
     c.rank = rank; c.world = world;
     if (world <= 1) return GPIRT_B200_OK;
     GP_TRY(load_api());
+    std::lock_guard<std::mutex> lock(g_comm_mu);
     if (!unique_id128) {
-        if (g_cached.comm && g_cached.rank == rank && g_cached.world == world) { c.nccl_comm = g_cached.comm; return GPIRT_B200_OK; }
+        if (g_cached.comm && g_cached.rank == rank && g_cached.world == world) {
+            c.nccl_comm = g_cached.comm;
+            g_cached.users += 1;
+            return GPIRT_B200_OK;
+        }
         set_last_error("world_size > 1 needs opts.nccl_unique_id (no cached communicator for rank %d of %d)", rank, world);
+        return GPIRT_B200_ERR_ARG;
+    }
+    if (g_cached.comm && g_cached.users > 0) {
+        set_last_error("a new nccl_unique_id was passed while %d live sampler(s) still use the cached communicator", g_cached.users);
         return GPIRT_B200_ERR_ARG;
     }
     if (g_cached.comm) { api.destroy(g_cached.comm); g_cached.comm = nullptr; }
     ncclUniqueId_t id;
     std::memcpy(&id, unique_id128, sizeof(id));
     GP_TRY(check(api.init_rank(&c.nccl_comm, world, id, rank), "ncclCommInitRank"));
-    g_cached.comm = c.nccl_comm; g_cached.rank = rank; g_cached.world = world;
+    g_cached.comm = c.nccl_comm; g_cached.rank = rank; g_cached.world = world; g_cached.users = 1;
     return GPIRT_B200_OK;
 }
 
@@ -91,11 +107,21 @@ int comm_allgather_f64(Comm& c, double* buf, size_t count_per_rank, cudaStream_t
     return check(api.allgather(buf + (size_t)c.rank * count_per_rank, buf, count_per_rank, ncclFloat64, c.nccl_comm, stream), "ncclAllGather");
 }
 
-void comm_destroy(Comm& c) { c.nccl_comm = nullptr; }   // the cached communicator stays alive for the next call
+void comm_destroy(Comm& c) {   // the cached communicator stays alive for the next call
+    std::lock_guard<std::mutex> lock(g_comm_mu);
+    if (c.nccl_comm && c.nccl_comm == g_cached.comm && g_cached.users > 0) g_cached.users -= 1;
+    c.nccl_comm = nullptr;
+}
 
-void comm_shutdown() {
+int comm_shutdown() {
+    std::lock_guard<std::mutex> lock(g_comm_mu);
+    if (g_cached.users > 0) {
+        set_last_error("%d live sampler(s) still use the NCCL communicator", g_cached.users);
+        return GPIRT_B200_ERR_ARG;
+    }
     if (g_cached.comm && api.destroy) api.destroy(g_cached.comm);
     g_cached.comm = nullptr; g_cached.rank = -1; g_cached.world = 0;
+    return GPIRT_B200_OK;
 }
 
 }  // namespace gpirt

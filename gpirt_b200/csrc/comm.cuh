@@ -16,6 +16,6 @@ int comm_allreduce_sum_f64(Comm& c, double* buf, size_t count, cudaStream_t stre
 // in-place all-gather: rank r contributes buf[r * count_per_rank, (r+1) * count_per_rank)
 int comm_allgather_f64(Comm& c, double* buf, size_t count_per_rank, cudaStream_t stream);
 void comm_destroy(Comm& c);
-void comm_shutdown();   // destroys the cached communicator
+int comm_shutdown();    // destroys the cached communicator (refused while a live sampler still holds it)
 
 }  // namespace gpirt

@@ -1,7 +1,9 @@
 // Shared host/device helpers for the gpirt_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -38,18 +40,26 @@ __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_
 int pool_alloc(void** p, size_t bytes, cudaStream_t st);
 void pool_free(void* p, cudaStream_t st);
 
-// Function attributes (dynamic shared memory limits) are per device: `flags` is a function-local static array; returns
-// true the first time the calling code runs on the current device.
-inline bool first_use_on_device(bool (&flags)[64]) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-    if (flags[dev]) return false;
-    flags[dev] = true;
-    return true;
-}
+// Function attributes (dynamic shared memory limits) are per device and must be set before the first launch from ANY
+// host thread: `flags` is a function-local static array; the guard serialises the check and the initialisation that
+// follows it in the caller's scope (`first` is true exactly once per device), so a second thread cannot launch between
+// the check and the attribute call.      { DeviceOnce once(flags); if (once.first) GP_CUDA(cudaFuncSetAttribute(...)); }
+std::mutex& device_once_mutex();
+struct DeviceOnce {
+    std::unique_lock<std::mutex> lock;
+    bool* slot = nullptr;
+    bool first = true;
+    explicit DeviceOnce(bool (&flags)[64]) : lock(device_once_mutex()) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+        slot = &flags[dev];
+        first = !*slot;
+    }
+    ~DeviceOnce() { if (slot) *slot = true; }
+};
 
 // launch counter (gpu_launches in bench.py): every kernel launch in this library goes through GP_LAUNCH
-extern int64_t g_launch_count;
+extern std::atomic<int64_t> g_launch_count;
 #define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
     do {                                                                                           \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \

@@ -456,14 +456,19 @@ int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double
         set_last_error("dgemm_i8: operands do not match");
         return GPIRT_B200_ERR_ARG;
     }
-    static int n_sm = 0;
+    static int sm_count[64] = {0};
     static bool attr_set[64] = {false};
-    if (first_use_on_device(attr_set)) {
-        int dev = 0;
-        GP_CUDA(cudaGetDevice(&dev));
-        GP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        GP_CUDA(cudaFuncSetAttribute(k_dgemm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+    int dev = 0;
+    GP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_last_error("dgemm_i8: device ordinal out of range"); return GPIRT_B200_ERR_ARG; }
+    {
+        DeviceOnce once(attr_set);
+        if (once.first) {
+            GP_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+            GP_CUDA(cudaFuncSetAttribute(k_dgemm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+        }
     }
+    const int n_sm = sm_count[dev];
     TileSched sched;
     sched.mtiles = (int)(A.rows_pad / DG_BM);
     sched.ntiles = (int)(B.rows_pad / DG_BN);

@@ -9,8 +9,10 @@ static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
     auto kern = gemm_f64_kernel<BM, BN, WM, WN, TA, TB, BABS>;
     static bool configured[64] = {false};  // per instantiation and device
     constexpr size_t smem = gemm_smem_bytes<BM, BN>();
-    if (first_use_on_device(configured))
-        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        DeviceOnce once(configured);
+        if (once.first) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     dim3 grid((unsigned)(ceil_div(g.N, BN) * ceil_div(g.M, BM)), 1, (unsigned)g.batch);
     GP_LAUNCH(kern, grid, dim3(WM * WN * 32), smem, stream, g);
     GP_CUDA(cudaGetLastError());

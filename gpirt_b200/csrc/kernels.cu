@@ -65,7 +65,7 @@ int launch_grid_init(cudaStream_t st, double* theta_star, double* prior) {
 __global__ void k_ingest_y(const double* __restrict__ y, int n, int m, int8_t* __restrict__ y8, int64_t ldy8,
                            double* __restrict__ yd, int64_t ldyd, unsigned long long* n_missing,
                            unsigned long long* n_bad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x, j = blockIdx.x;   // items on grid.x (2^31-1), rows on grid.y
     if (i >= n) return;
     const double v = y[i + (int64_t)j * n];
     int8_t c = 0;
@@ -78,7 +78,7 @@ __global__ void k_ingest_y(const double* __restrict__ y, int n, int m, int8_t* _
 }
 int launch_ingest_y(cudaStream_t st, const double* y, int n, int m, int8_t* y8, int64_t ldy8, double* yd, int64_t ldyd,
                     unsigned long long* n_missing, unsigned long long* n_bad) {
-    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)m);
+    dim3 grid((unsigned)m, (unsigned)ceil_div(n, 256));
     GP_LAUNCH(k_ingest_y, grid, 256, 0, st, y, n, m, y8, ldy8, yd, ldyd, n_missing, n_bad);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -89,7 +89,7 @@ int launch_ingest_y(cudaStream_t st, const double* y, int n, int m, int8_t* y8, 
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fill_normal(double* __restrict__ Z, int n, int64_t ld, RngKey key,
                                                      uint32_t purpose, uint32_t item_offset) {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int pair = blockIdx.y * blockDim.x + threadIdx.x, j = blockIdx.x;
     const int i0 = 2 * pair;
     if (i0 >= n) return;
     double za, zb;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_fill_normal(double* __restrict__ Z, int
 int launch_fill_normal(cudaStream_t st, double* Z, int n, int m, int64_t ld, RngKey key, uint32_t purpose,
                        uint32_t item_offset) {
     if (n <= 0 || m <= 0) return GPIRT_B200_OK;
-    dim3 grid((unsigned)ceil_div(ceil_div(n, 2), 256), (unsigned)m);
+    dim3 grid((unsigned)m, (unsigned)ceil_div(ceil_div(n, 2), 256));
     GP_LAUNCH(k_fill_normal, grid, 256, 0, st, Z, n, ld, key, purpose, item_offset);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_fill_normal_planes(int8_t* __restrict__
                                                             int64_t rows_pad, int64_t k_pad, int n, RngKey key,
                                                             uint32_t purpose, uint32_t item_offset,
                                                             double* __restrict__ Z, int64_t ld) {
-    const int quad = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int quad = blockIdx.y * blockDim.x + threadIdx.x, j = blockIdx.x;
     const int i0 = 4 * quad;
     if (quad == 0) scale[j] = 0.25;                 // 2^(Z_FIXED_EXP - 6)
     if (i0 >= n) return;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) k_fill_normal_planes(int8_t* __restrict__
 int launch_fill_normal_planes(cudaStream_t st, int8_t* planes, double* scale, int64_t rows_pad, int64_t k_pad, int n, int m,
                               RngKey key, uint32_t purpose, uint32_t item_offset, double* Z_or_null, int64_t ld) {
     if (n <= 0 || m <= 0) return GPIRT_B200_OK;
-    dim3 grid((unsigned)ceil_div(ceil_div(n, 4), 256), (unsigned)m);
+    dim3 grid((unsigned)m, (unsigned)ceil_div(ceil_div(n, 4), 256));
     GP_LAUNCH(k_fill_normal_planes, grid, 256, 0, st, planes, scale, rows_pad, k_pad, n, key, purpose, item_offset, Z_or_null, ld);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -179,11 +179,14 @@ int launch_rng_probe(cudaStream_t st, RngKey key, uint32_t purpose, uint32_t str
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Elliptical slice sampler, one CTA per item (reference src/draw-f.cpp:21-60, likelihood src/log-likelihood.cpp:25-37).
-// The item's f, nu, y and the linear mean mu_i = beta0 + beta1 theta_i stay in registers (EPT values per thread) for
-// the whole data-dependent shrink loop, so HBM is touched once on the way in and once on the way out.  The block-wide
-// log-likelihood sum is a fixed-order shuffle + shared-memory reduction (every thread ends with the same bits, so the
-// accept test needs no broadcast); the uniforms come from Philox by address, recomputed by every thread.
+// Elliptical slice sampler (reference src/draw-f.cpp:21-60, likelihood src/log-likelihood.cpp:25-37) and beta Metropolis
+// step (src/draw-beta.cpp:16-38): ONE __device__ body each (ess_item, beta_item), shared by three launch shapes
+//   k_*          one CTA per item, the item's columns in registers (EPT values per thread)
+//   k_*_persist  one CTA per SM claims items from an atomic counter and cp.async-prefetches the next item's columns
+//   k_*_stream   n > 4096: the item no longer fits the register file of a CTA; every evaluation re-streams it from L2
+// The shapes differ only in where a thread's cells come from (the Cur / Prop / Eval functors below).
+// The block-wide log-likelihood sum is a fixed-order shuffle + shared-memory reduction (every thread ends with the same
+// bits, so the accept test needs no broadcast); the uniforms come from Philox by address, recomputed by every thread.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ESS_ITER_CAP = 10000;
 
@@ -195,45 +198,25 @@ __device__ __forceinline__ double obs_term(const double* __restrict__ sp, double
     return (y != 0.0) ? t : 0.0;
 }
 
-template <int EPT, int MAXT>
-__global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
-                      int64_t ldy, const double* __restrict__ theta, const double* __restrict__ beta, int n, RngKey key,
-                      uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status,
-                      const double* __restrict__ sp) {
-    __shared__ double red[2][32];
-    __shared__ double nxt[2][4];   // speculative next proposal: angle, sine, cosine (double-buffered like red)
-    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const uint32_t item = item_offset + (uint32_t)j;
-    const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
-    double fv[EPT], nv[EPT], gm[EPT], yv[EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int i = tid + e * T;
-        if (i < n) {
-            fv[e] = f[i + (int64_t)j * ld];
-            nv[e] = nu[i + (int64_t)j * ld];
-            yv[e] = (double)y8[i + (int64_t)j * ldy];
-            gm[e] = fma(theta[i], b1, b0);
-        } else { fv[e] = nv[e] = gm[e] = yv[e] = 0.0; }
-    }
-    double part = 0.0;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e)
-        part -= obs_term(sp, yv[e], yv[e] * (fv[e] + gm[e]));
-    const double ll_cur = block_sum(part, red[0]);
-    const double u = rng_uniform(key, P_ESS_U, item, 0u);
-    const double log_y = ll_cur + log(u);                                            // draw-f.cpp:28-29
+// One item's slice step.  cur() -> this thread's partial of ll_bar(f, y, mu);  prop(c, s) -> its partial of
+// ll_bar(f c + nu s, y, mu).  Returns the number of proposals; (c_out, s_out) = cosine / sine of the accepted angle.
+// The angle of proposal t+1 does not depend on the likelihood of proposal t, only on its being rejected: the shrunk
+// bracket, the next Philox uniform, the next angle and its sine / cosine are computed by warp 0 WHILE proposal t is
+// evaluated and published through shared memory ahead of the barrier of the block sum, so the serial part of a round
+// is the reduction alone.  Same formulas, same bits as the sequential loop.
+template <class Cur, class Prop>
+__device__ __forceinline__ int ess_item(const RngKey& key, uint32_t item, double (*red)[32], double (*nxt)[4], int* status,
+                                        Cur&& cur, Prop&& prop, double& c_out, double& s_out) {
+    const int tid = threadIdx.x;
+    const double ll_cur = block_sum(cur(), red[0]);
+    const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));             // draw-f.cpp:28-29
     const double TWO_PI = 6.283185307179586476925286766559;
-    double eps_min = 0.0, eps_max = TWO_PI;                                          // :33-34
-    double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u); // :35 R::runif(a,b) = a + (b-a) u
-    eps_min = eps - TWO_PI;                                                          // :36 (eps_max stays 2 pi)
+    double eps_min = 0.0, eps_max = TWO_PI;                                             // :33-34
+    double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u);   // :35 R::runif(a,b) = a + (b-a) u
+    eps_min = eps - TWO_PI;                                                             // :36 (eps_max stays 2 pi)
     int iter = 0;
     double s, c;
     sincos(eps, &s, &c);
-    // The angle of proposal t+1 does not depend on the likelihood of proposal t, only on its being rejected: the shrunk
-    // bracket, the next Philox uniform, the next angle and its sine / cosine are computed by warp 0 WHILE proposal t is
-    // evaluated and published through shared memory ahead of the barrier of the block sum, so the serial part of a
-    // round is the reduction alone.  Same formulas, same bits as the sequential loop.
     const bool leader = tid < 32;
     for (;;) {
         iter += 1;
@@ -244,82 +227,114 @@ __global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const doub
             sincos(eps_n, &sn, &cn);
             if (tid == 0) { nxt[iter & 1][0] = eps_n; nxt[iter & 1][1] = sn; nxt[iter & 1][2] = cn; }
         }
-        part = 0.0;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-            {
-                const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
-                part -= obs_term(sp, yv[e], yv[e] * (fp + gm[e]));
-            }
-        const double ll_new = block_sum(part, red[iter & 1]);
-        if (ll_new > log_y) break;                                                   // :45 strict
+        const double ll_new = block_sum(prop(c, s), red[iter & 1]);
+        if (ll_new > log_y) break;                                                      // :45 strict
         eps_min = emin_n; eps_max = emax_n;
         eps = nxt[iter & 1][0]; s = nxt[iter & 1][1]; c = nxt[iter & 1][2];
-        if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }    // NaN likelihood: reference would spin
+        if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }       // NaN likelihood: reference would spin
     }
+    c_out = c; s_out = s;
+    return iter;
+}
+
+// an item's cells held in registers: value e of thread tid is respondent tid + e * blockDim.x
+template <int EPT> struct ItemRegs {
+    double fv[EPT], nv[EPT], gm[EPT], yv[EPT];
+    __device__ __forceinline__ double cur(const double* __restrict__ sp) const {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) part -= obs_term(sp, yv[e], yv[e] * (fv[e] + gm[e]));
+        return part;
+    }
+    __device__ __forceinline__ double prop(const double* __restrict__ sp, double c, double s) const {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));      // :43, no FMA contraction
+            part -= obs_term(sp, yv[e], yv[e] * (fp + gm[e]));
+        }
+        return part;
+    }
+    __device__ __forceinline__ void store(double* __restrict__ fj, int n, double c, double s) const {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            if (i < n) fj[i] = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));
+        }
+    }
+};
+
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_ess(double* __restrict__ f, const double* __restrict__ nu, int64_t ld, const int8_t* __restrict__ y8,
+                      int64_t ldy, const double* __restrict__ theta, const double* __restrict__ beta, int n, RngKey key,
+                      uint32_t item_offset, int* __restrict__ nprop, int* __restrict__ status,
+                      const double* __restrict__ sp) {
+    __shared__ double red[2][32];
+    __shared__ double nxt[2][4];   // speculative next proposal: angle, sine, cosine (double-buffered like red)
+    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
+    ItemRegs<EPT> it;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const int i = tid + e * T;
-        if (i < n) f[i + (int64_t)j * ld] = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));
+        if (i < n) {
+            it.fv[e] = f[i + (int64_t)j * ld];
+            it.nv[e] = nu[i + (int64_t)j * ld];
+            it.yv[e] = (double)y8[i + (int64_t)j * ldy];
+            it.gm[e] = fma(theta[i], b1, b0);
+        } else { it.fv[e] = it.nv[e] = it.gm[e] = it.yv[e] = 0.0; }
     }
+    double c, s;
+    const int iter = ess_item(key, item_offset + (uint32_t)j, red, nxt, status, [&] { return it.cur(sp); },
+                              [&](double cc, double ss) { return it.prop(sp, cc, ss); }, c, s);
+    it.store(f + (int64_t)j * ld, n, c, s);
     if (tid == 0 && nprop) nprop[j] = iter;
 }
 
-// Large-n variant (n > 4096: the item no longer fits the register file of one CTA): same algorithm, but every
-// proposal re-streams f, nu, y, theta from L2 (the 17n bytes of an item stay L2-resident across its shrink loop).
+// Large-n shape (n > 4096): same body, but every evaluation re-streams f, nu, y, theta from L2 (the 17n bytes of an item
+// stay L2-resident across its shrink loop).
 __global__ void __launch_bounds__(1024) k_ess_stream(double* __restrict__ f, const double* __restrict__ nu, int64_t ld,
                                                      const int8_t* __restrict__ y8, int64_t ldy,
                                                      const double* __restrict__ theta, const double* __restrict__ beta,
                                                      int n, RngKey key, uint32_t item_offset, int* __restrict__ nprop,
                                                      int* __restrict__ status, const double* __restrict__ sp) {
     __shared__ double red[2][32];
+    __shared__ double nxt[2][4];
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const uint32_t item = item_offset + (uint32_t)j;
     const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
     double* fj = f + (int64_t)j * ld;
     const double* nj = nu + (int64_t)j * ld;
     const int8_t* yj = y8 + (int64_t)j * ldy;
-    double part = 0.0;
-    for (int i = tid; i < n; i += T) {
-        const double yv = (double)yj[i];
-        if (yv != 0.0) part -= ll_term_fast(sp, yv * (fj[i] + fma(theta[i], b1, b0)));
-    }
-    const double ll_cur = block_sum(part, red[0]);
-    const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));
-    const double TWO_PI = 6.283185307179586476925286766559;
-    double eps_min = 0.0, eps_max = TWO_PI;
-    double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u);
-    eps_min = eps - TWO_PI;
-    int iter = 0;
-    double s, c;
-    for (;;) {
-        iter += 1;
-        sincos(eps, &s, &c);
-        part = 0.0;
+    auto cur = [&] {
+        double part = 0.0;
+#pragma unroll 4
         for (int i = tid; i < n; i += T) {
             const double yv = (double)yj[i];
-            if (yv != 0.0) {
-                const double fp = __dadd_rn(__dmul_rn(fj[i], c), __dmul_rn(nj[i], s));
-                part -= ll_term_fast(sp, yv * (fp + fma(theta[i], b1, b0)));
-            }
+            part -= obs_term(sp, yv, yv * (fj[i] + fma(theta[i], b1, b0)));
         }
-        const double ll_new = block_sum(part, red[iter & 1]);
-        if (ll_new > log_y) break;
-        if (eps < 0.0) eps_min = eps; else eps_max = eps;
-        eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);
-        if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }
-    }
+        return part;
+    };
+    auto prop = [&](double c, double s) {
+        double part = 0.0;
+#pragma unroll 4
+        for (int i = tid; i < n; i += T) {
+            const double yv = (double)yj[i];
+            const double fp = __dadd_rn(__dmul_rn(fj[i], c), __dmul_rn(nj[i], s));
+            part -= obs_term(sp, yv, yv * (fp + fma(theta[i], b1, b0)));
+        }
+        return part;
+    };
+    double c, s;
+    const int iter = ess_item(key, item_offset + (uint32_t)j, red, nxt, status, cur, prop, c, s);
     for (int i = tid; i < n; i += T) fj[i] = __dadd_rn(__dmul_rn(fj[i], c), __dmul_rn(nj[i], s));
     if (tid == 0 && nprop) nprop[j] = iter;
 }
 
-
-// ---- persistent variant ---------------------------------------------------------------------------------------------
+// ---- persistent shape -----------------------------------------------------------------------------------------------
 // One CTA per SM walks the item list (next item claimed with an atomic counter, so the data-dependent proposal counts
 // balance themselves) and the NEXT item's f, nu and y columns are fetched into shared memory with cp.async while the
 // current item's shrink loop runs: with one register-heavy CTA per SM the HBM latency of every item's loads was fully
-// exposed (ncu: a quarter of all stall samples sat on the first use of the loaded columns).  theta is read once per
-// CTA.  Same arithmetic, same bits as k_ess.
+// exposed (ncu: a quarter of all stall samples sat on the first use of the loaded columns).  theta is read once per CTA.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -362,60 +377,22 @@ __global__ void __launch_bounds__(MAXT) k_ess_persist(double* __restrict__ f, co
         const int jn = s_next;
         if (jn < m) { prefetch(jn, b ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();
-        const uint32_t item = item_offset + (uint32_t)j;
         const double b0 = beta[2 * j], b1 = beta[2 * j + 1];
-        double fv[EPT], nv[EPT], gm[EPT], yv[EPT];
+        ItemRegs<EPT> it;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int i = tid + e * T;
             if (i < n) {
-                fv[e] = fbuf[b * NP + i];
-                nv[e] = nbuf[b * NP + i];
-                yv[e] = (double)ybuf[b * NP + i];
-                gm[e] = fma(th[e], b1, b0);
-            } else { fv[e] = nv[e] = gm[e] = yv[e] = 0.0; }
+                it.fv[e] = fbuf[b * NP + i];
+                it.nv[e] = nbuf[b * NP + i];
+                it.yv[e] = (double)ybuf[b * NP + i];
+                it.gm[e] = fma(th[e], b1, b0);
+            } else { it.fv[e] = it.nv[e] = it.gm[e] = it.yv[e] = 0.0; }
         }
-        double part = 0.0;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-            part -= obs_term(sp, yv[e], yv[e] * (fv[e] + gm[e]));
-        const double ll_cur = block_sum(part, red[0]);
-        const double log_y = ll_cur + log(rng_uniform(key, P_ESS_U, item, 0u));          // draw-f.cpp:28-29
-        const double TWO_PI = 6.283185307179586476925286766559;
-        double eps_min = 0.0, eps_max = TWO_PI;                                          // :33-34
-        double eps = eps_min + (eps_max - eps_min) * rng_uniform(key, P_ESS_U, item, 1u); // :35
-        eps_min = eps - TWO_PI;                                                          // :36
-        int iter = 0;
-        double s, c;
-        sincos(eps, &s, &c);
-        const bool leader = tid < 32;
-        for (;;) {
-            iter += 1;
-            const double emin_n = (eps < 0.0) ? eps : eps_min, emax_n = (eps < 0.0) ? eps_max : eps;   // :50-55 if rejected
-            if (leader) {
-                const double eps_n = emin_n + (emax_n - emin_n) * rng_uniform(key, P_ESS_U, item, 1u + (uint32_t)iter);  // :56
-                double sn, cn;
-                sincos(eps_n, &sn, &cn);
-                if (tid == 0) { nxt[iter & 1][0] = eps_n; nxt[iter & 1][1] = sn; nxt[iter & 1][2] = cn; }
-            }
-            part = 0.0;
-#pragma unroll
-            for (int e = 0; e < EPT; ++e)
-                {
-                    const double fp = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));  // :43, no FMA contraction
-                    part -= obs_term(sp, yv[e], yv[e] * (fp + gm[e]));
-                }
-            const double ll_new = block_sum(part, red[iter & 1]);
-            if (ll_new > log_y) break;                                                   // :45 strict
-            eps_min = emin_n; eps_max = emax_n;
-            eps = nxt[iter & 1][0]; s = nxt[iter & 1][1]; c = nxt[iter & 1][2];
-            if (iter >= ESS_ITER_CAP) { if (tid == 0) atomicExch(status, 1); break; }
-        }
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            const int i = tid + e * T;
-            if (i < n) f[i + (int64_t)j * ld] = __dadd_rn(__dmul_rn(fv[e], c), __dmul_rn(nv[e], s));
-        }
+        double c, s;
+        const int iter = ess_item(key, item_offset + (uint32_t)j, red, nxt, status, [&] { return it.cur(sp); },
+                                  [&](double cc, double ss) { return it.prop(sp, cc, ss); }, c, s);
+        it.store(f + (int64_t)j * ld, n, c, s);
         if (tid == 0 && nprop) nprop[j] = iter;
         j = jn;
         b ^= 1;
@@ -476,7 +453,7 @@ static void item_cta_shape(int n, int& ept, int& threads) {
 
 int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const int8_t* y8, int64_t ldy,
                const double* theta, const double* beta, int n, int m, RngKey key, uint32_t item_offset, int* nprop,
-               int* status, int* work) {
+               int* status, int* work, int* shape) {
     if (m <= 0) return GPIRT_B200_OK;
     int ept, threads;
     item_cta_shape(n, ept, threads);
@@ -491,8 +468,9 @@ int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const i
             default: ESS_PERSIST_CASE(8, 512) break;
         }
         GP_CUDA(cudaGetLastError());
-        if (launched) return GPIRT_B200_OK;
+        if (launched) { if (shape) *shape = ITEM_SHAPE_PERSISTENT; return GPIRT_B200_OK; }
     }
+    if (shape) *shape = ept ? ITEM_SHAPE_CTA : ITEM_SHAPE_STREAM;
     switch (ept) {
         case 1: GP_LAUNCH((k_ess<1, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
         case 2: GP_LAUNCH((k_ess<2, 512>), m, threads, 0, st, f, nu, ld, y8, ldy, theta, beta, n, key, item_offset, nprop, status, sp); break;
@@ -531,7 +509,7 @@ __global__ void __launch_bounds__(256) k_fstar_finish(double* __restrict__ fstar
                                                       const double* __restrict__ beta, const double* __restrict__ theta_star,
                                                       RngKey key, uint32_t item_offset, double* __restrict__ irf_sum,
                                                       int accumulate) {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int pair = blockIdx.y * blockDim.x + threadIdx.x, j = blockIdx.x;
     const int k0 = 2 * pair;
     if (k0 >= N) return;
     double za, zb;
@@ -554,21 +532,21 @@ __global__ void __launch_bounds__(256) k_fstar_finish(double* __restrict__ fstar
 int launch_fstar_finish(cudaStream_t st, double* fstar, int64_t ld, int N, int m, const double* s, const double* beta,
                         const double* theta_star, RngKey key, uint32_t item_offset, double* irf_sum, int accumulate) {
     if (m <= 0) return GPIRT_B200_OK;
-    dim3 grid((unsigned)ceil_div(ceil_div(N, 2), 256), (unsigned)m);
+    dim3 grid((unsigned)m, (unsigned)ceil_div(ceil_div(N, 2), 256));
     GP_LAUNCH(k_fstar_finish, grid, 256, 0, st, fstar, ld, N, s, beta, theta_star, key, item_offset, irf_sum, accumulate);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
 }
 
 __global__ void k_irf_finish(const double* __restrict__ irf_sum, int64_t ld, int N, double inv_samples, double* __restrict__ out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x, j = blockIdx.x;
     if (k >= N) return;
     const double x = irf_sum[k + (int64_t)j * ld] * inv_samples;                   // gpirtMCMC.cpp:106
     out[k + (int64_t)j * N] = 1.0 / (1.0 + exp(-x));                               // R::plogis, :109
 }
 int launch_irf_finish(cudaStream_t st, const double* irf_sum, int64_t ld, int N, int m, double inv_samples, double* out) {
     if (m <= 0) return GPIRT_B200_OK;
-    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)m);
+    dim3 grid((unsigned)m, (unsigned)ceil_div(N, 256));
     GP_LAUNCH(k_irf_finish, grid, 256, 0, st, irf_sum, ld, N, inv_samples, out);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -705,24 +683,17 @@ __device__ __forceinline__ double dnorm_log(double x, double mu, double sd) {  /
     return -(0.918938533204672741780329736406 + 0.5 * t * t + log(sd));
 }
 
-template <int EPT, int MAXT>
-__global__ void __launch_bounds__(MAXT) k_beta(double* __restrict__ beta, const double* __restrict__ f, int64_t ld, const int8_t* __restrict__ y8,
-                       int64_t ldy, const double* __restrict__ theta, const double* __restrict__ pm,
-                       const double* __restrict__ psd, const double* __restrict__ pstep, int n, RngKey key,
-                       uint32_t item_offset, const double* __restrict__ sp) {
-    __shared__ double red[4][32];
-    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const uint32_t item = item_offset + (uint32_t)j;
-    double fv[EPT], th[EPT], yv[EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int i = tid + e * T;
-        if (i < n) { fv[e] = f[i + (int64_t)j * ld]; th[e] = theta[i]; yv[e] = (double)y8[i + (int64_t)j * ldy]; }
-        else { fv[e] = th[e] = yv[e] = 0.0; }
-    }
+// One item's Metropolis step for the two mean coefficients (draw-beta.cpp:16-38).
+//   eval(p0, p1, c0, c1, with_c, part_p, part_c): this thread's partials of ll_bar(f, y, X (p0,p1)^T) and, if with_c,
+//   of ll_bar(f, y, X (c0,c1)^T), evaluated in one pass over its cells.
+// The reference recomputes ll_bar(f, y, X cv) for k = 1 (:28); it is the value kept from k = 0 (same inputs, same bits).
+template <class Eval>
+__device__ __forceinline__ void beta_item(const RngKey& key, uint32_t item, int j, double* __restrict__ beta,
+                                          const double* __restrict__ pm, const double* __restrict__ psd,
+                                          const double* __restrict__ pstep, double (*red)[32], Eval&& eval) {
     double cv[2] = {beta[2 * j], beta[2 * j + 1]};
     double pv[2] = {cv[0], cv[1]};
-    double cv_ll = 0.0;   // ll_bar(rho, y, X * cv): the reference recomputes it for k = 1 (:28); it is the value kept from k = 0
+    double cv_ll = 0.0;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
@@ -730,23 +701,48 @@ __global__ void __launch_bounds__(MAXT) k_beta(double* __restrict__ beta, const 
         const double pv_prior = dnorm_log(pv[k], pm[2 * j + k], psd[2 * j + k]);    // :25
         const double cv_prior = dnorm_log(cv[k], pm[2 * j + k], psd[2 * j + k]);    // :26
         double part_p = 0.0, part_c = 0.0;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-            {
-                part_p -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27  ll_bar(rho, y, X * pv)
-                if (k == 0) part_c -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
-            }
+        eval(pv[0], pv[1], cv[0], cv[1], k == 0, part_p, part_c);                   // :27 (and :28 for k = 0)
         const double pv_ll = block_sum(part_p, red[2 * k]);
         if (k == 0) cv_ll = block_sum(part_c, red[2 * k + 1]);
         const double r = pv_prior + pv_ll - cv_prior - cv_ll;                       // :29
         const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
         if (log(u) < r) { cv[k] = pv[k]; cv_ll = pv_ll; } else pv[k] = cv[k];       // :30-35
     }
-    if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
+    if (threadIdx.x == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
 }
 
+// an item's f, y and the respondents' theta held in registers
+template <int EPT> struct BetaRegs {
+    double fv[EPT], th[EPT], yv[EPT];
+    __device__ __forceinline__ void eval(const double* __restrict__ sp, double p0, double p1, double c0, double c1, bool with_c,
+                                         double& part_p, double& part_c) const {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            part_p -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], p1, p0)));
+            if (with_c) part_c -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], c1, c0)));
+        }
+    }
+};
 
-// persistent variant of the beta step (see k_ess_persist): next item's f and y columns prefetched, theta read once
+template <int EPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_beta(double* __restrict__ beta, const double* __restrict__ f, int64_t ld, const int8_t* __restrict__ y8,
+                       int64_t ldy, const double* __restrict__ theta, const double* __restrict__ pm,
+                       const double* __restrict__ psd, const double* __restrict__ pstep, int n, RngKey key,
+                       uint32_t item_offset, const double* __restrict__ sp) {
+    __shared__ double red[4][32];
+    const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    BetaRegs<EPT> it;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * T;
+        if (i < n) { it.fv[e] = f[i + (int64_t)j * ld]; it.th[e] = theta[i]; it.yv[e] = (double)y8[i + (int64_t)j * ldy]; }
+        else { it.fv[e] = it.th[e] = it.yv[e] = 0.0; }
+    }
+    beta_item(key, item_offset + (uint32_t)j, j, beta, pm, psd, pstep, red,
+              [&](double p0, double p1, double c0, double c1, bool wc, double& pp, double& pc) { it.eval(sp, p0, p1, c0, c1, wc, pp, pc); });
+}
+
+// persistent shape of the beta step (see k_ess_persist): next item's f and y columns prefetched, theta read once
 template <int EPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) k_beta_persist(double* __restrict__ beta, const double* __restrict__ f, int64_t ld,
                                                        const int8_t* __restrict__ y8, int64_t ldy, const double* __restrict__ theta,
@@ -759,9 +755,9 @@ __global__ void __launch_bounds__(MAXT) k_beta_persist(double* __restrict__ beta
     const int tid = threadIdx.x, T = blockDim.x, NP = EPT * T;
     double* fbuf = reinterpret_cast<double*>(dsm);
     int8_t* ybuf = reinterpret_cast<int8_t*>(fbuf + 2 * NP);
-    double th[EPT];
+    BetaRegs<EPT> it;
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) { const int i = tid + e * T; th[e] = (i < n) ? theta[i] : 0.0; }
+    for (int e = 0; e < EPT; ++e) { const int i = tid + e * T; it.th[e] = (i < n) ? theta[i] : 0.0; }
     auto prefetch = [&](int j, int b) {
         const double* fs = f + (int64_t)j * ld;
         const int8_t* ys = y8 + (int64_t)j * ldy;
@@ -777,37 +773,14 @@ __global__ void __launch_bounds__(MAXT) k_beta_persist(double* __restrict__ beta
         const int jn = s_next;
         if (jn < m) { prefetch(jn, b ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();
-        const uint32_t item = item_offset + (uint32_t)j;
-        double fv[EPT], yv[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int i = tid + e * T;
-            if (i < n) { fv[e] = fbuf[b * NP + i]; yv[e] = (double)ybuf[b * NP + i]; }
-            else { fv[e] = yv[e] = 0.0; }
+            if (i < n) { it.fv[e] = fbuf[b * NP + i]; it.yv[e] = (double)ybuf[b * NP + i]; }
+            else { it.fv[e] = it.yv[e] = 0.0; }
         }
-        double cv[2] = {beta[2 * j], beta[2 * j + 1]};
-        double pv[2] = {cv[0], cv[1]};
-        double cv_ll = 0.0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
-            pv[k] = __dadd_rn(cv[k], __dmul_rn(pstep[2 * j + k], z));                   // :22
-            const double pv_prior = dnorm_log(pv[k], pm[2 * j + k], psd[2 * j + k]);    // :25
-            const double cv_prior = dnorm_log(cv[k], pm[2 * j + k], psd[2 * j + k]);    // :26
-            double part_p = 0.0, part_c = 0.0;
-#pragma unroll
-            for (int e = 0; e < EPT; ++e)
-                {
-                    part_p -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], pv[1], pv[0])));      // :27
-                    if (k == 0) part_c -= obs_term(sp, yv[e], yv[e] * (fv[e] + fma(th[e], cv[1], cv[0])));   // :28
-                }
-            const double pv_ll = block_sum(part_p, red[2 * k]);
-            if (k == 0) cv_ll = block_sum(part_c, red[2 * k + 1]);
-            const double r = pv_prior + pv_ll - cv_prior - cv_ll;                       // :29
-            const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
-            if (log(u) < r) { cv[k] = pv[k]; cv_ll = pv_ll; } else pv[k] = cv[k];       // :30-35
-        }
-        if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
+        beta_item(key, item_offset + (uint32_t)j, j, beta, pm, psd, pstep, red,
+                  [&](double p0, double p1, double c0, double c1, bool wc, double& pp, double& pc) { it.eval(sp, p0, p1, c0, c1, wc, pp, pc); });
         j = jn;
         b ^= 1;
     }
@@ -821,33 +794,17 @@ __global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta,
                                                       const double* __restrict__ sp) {
     __shared__ double red[4][32];
     const int j = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const uint32_t item = item_offset + (uint32_t)j;
     const double* fj = f + (int64_t)j * ld;
     const int8_t* yj = y8 + (int64_t)j * ldy;
-    double cv[2] = {beta[2 * j], beta[2 * j + 1]};
-    double pv[2] = {cv[0], cv[1]};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const double z = rng_normal(key, P_BETA_Z, item, (uint32_t)k);
-        pv[k] = __dadd_rn(cv[k], __dmul_rn(pstep[2 * j + k], z));
-        const double pv_prior = dnorm_log(pv[k], pm[2 * j + k], psd[2 * j + k]);
-        const double cv_prior = dnorm_log(cv[k], pm[2 * j + k], psd[2 * j + k]);
-        double part_p = 0.0, part_c = 0.0;
-        for (int i = tid; i < n; i += T) {
-            const double yv = (double)yj[i];
-            if (yv != 0.0) {
-                const double fi = fj[i], ti = theta[i];
-                part_p -= ll_term_fast(sp, yv * (fi + fma(ti, pv[1], pv[0])));
-                part_c -= ll_term_fast(sp, yv * (fi + fma(ti, cv[1], cv[0])));
-            }
-        }
-        const double pv_ll = block_sum(part_p, red[2 * k]);
-        const double cv_ll = block_sum(part_c, red[2 * k + 1]);
-        const double r = pv_prior + pv_ll - cv_prior - cv_ll;
-        const double u = rng_uniform(key, P_BETA_U, item, (uint32_t)k);
-        if (log(u) < r) cv[k] = pv[k]; else pv[k] = cv[k];
-    }
-    if (tid == 0) { beta[2 * j] = cv[0]; beta[2 * j + 1] = cv[1]; }
+    beta_item(key, item_offset + (uint32_t)j, j, beta, pm, psd, pstep, red,
+              [&](double p0, double p1, double c0, double c1, bool wc, double& pp, double& pc) {
+#pragma unroll 4
+                  for (int i = tid; i < n; i += T) {
+                      const double yv = (double)yj[i], fi = fj[i], ti = theta[i];
+                      pp -= obs_term(sp, yv, yv * (fi + fma(ti, p1, p0)));
+                      if (wc) pc -= obs_term(sp, yv, yv * (fi + fma(ti, c1, c0)));
+                  }
+              });
 }
 
 #define BETA_PERSIST_CASE(E, MT)                                                                                             \
@@ -865,7 +822,7 @@ __global__ void __launch_bounds__(1024) k_beta_stream(double* __restrict__ beta,
 
 int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, const int8_t* y8, int64_t ldy,
                 const double* theta, const double* pm, const double* psd, const double* pstep, int n, int m,
-                RngKey key, uint32_t item_offset, int* status, int* work) {
+                RngKey key, uint32_t item_offset, int* status, int* work, int* shape) {
     (void)status;
     if (m <= 0) return GPIRT_B200_OK;
     int ept, threads;
@@ -881,8 +838,9 @@ int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, cons
             default: BETA_PERSIST_CASE(8, 512) break;
         }
         GP_CUDA(cudaGetLastError());
-        if (launched) return GPIRT_B200_OK;
+        if (launched) { if (shape) *shape = ITEM_SHAPE_PERSISTENT; return GPIRT_B200_OK; }
     }
+    if (shape) *shape = ept ? ITEM_SHAPE_CTA : ITEM_SHAPE_STREAM;
     switch (ept) {
         case 1: GP_LAUNCH((k_beta<1, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;
         case 2: GP_LAUNCH((k_beta<2, 512>), m, threads, 0, st, beta, f, ld, y8, ldy, theta, pm, psd, pstep, n, key, item_offset, sp); break;

@@ -24,10 +24,13 @@ int launch_fill_normal_planes(cudaStream_t st, int8_t* planes, double* scale, in
 // beta[p,j] = pm + psd * z  (gpirtMCMC.cpp:23-27)
 int launch_init_beta(cudaStream_t st, double* beta, const double* pm, const double* psd, int m, RngKey key,
                      uint32_t item_offset);
+// launch shape the per-item kernels (ESS, beta) picked: one CTA per item with the item in registers, one persistent CTA
+// per SM with prefetch, or the n > 4096 streaming shape (reported through gpirt_b200_sampler_uses for the parity tests)
+enum ItemShape : int { ITEM_SHAPE_CTA = 0, ITEM_SHAPE_PERSISTENT = 1, ITEM_SHAPE_STREAM = 2 };
 // elliptical slice sampler for all items (draw-f.cpp); f updated in place
 int launch_ess(cudaStream_t st, double* f, const double* nu, int64_t ld, const int8_t* y8, int64_t ldy,
                const double* theta, const double* beta, int n, int m, RngKey key, uint32_t item_offset, int* nprop,
-               int* status, int* work = nullptr);   // work: one zeroable int (item counter of the persistent variant)
+               int* status, int* work = nullptr, int* shape = nullptr);   // work: one zeroable int (item counter of the persistent shape)
 // s_k = 1 - sqrt(sum_i tmp_ik^2)
 int launch_fstar_sd(cudaStream_t st, const double* tmp, int64_t ld, int n, int N, double* s);
 // f*_kj = (mean_kj + beta0_j + beta1_j theta*_k) + s_k z_kj, in place over mean; optional IRF accumulation
@@ -43,7 +46,7 @@ int launch_theta_draw(cudaStream_t st, const double* logPt, int64_t ld, const do
 // Metropolis step for the two mean coefficients of every item (draw-beta.cpp)
 int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, const int8_t* y8, int64_t ldy,
                 const double* theta, const double* pm, const double* psd, const double* pstep, int n, int m,
-                RngKey key, uint32_t item_offset, int* status, int* work = nullptr);
+                RngKey key, uint32_t item_offset, int* status, int* work = nullptr, int* shape = nullptr);
 // out[j] = ll_bar(f_j, y_j, mu_j) for explicit mu (host-API helper)
 int launch_ll_bar(cudaStream_t st, const double* f, const double* y, const double* mu, int n, int m, double* out);
 // IRF = plogis(sum / S)

@@ -7,13 +7,7 @@
 
 namespace gpirt {
 
-constexpr int DIAG_NB = 64;  // diagonal blocks factorised + inverted inside one CTA
-
-// In-place lower Cholesky of the n x n matrix A (only the lower triangle is read or written; whatever the caller
-// left in the strict upper triangle stays).  Dinv (n x 64, leading dimension ldd) receives the inverse of every
-// 64 x 64 diagonal block of L (block b at rows 64b..), which the triangular solves below consume.
-// d_status (device int) is set non-zero if a pivot is not positive (chol(): decomposition failed).
-int potrf_lower(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv, int64_t ldd, int* d_status);
+constexpr int DIAG_NB = 64;  // diagonal blocks inverted inside one CTA by the stand-alone triangular solve (gpirt_b200_trsm_lower)
 
 // Dinv <- inverses of the 64 x 64 diagonal blocks of an existing lower-triangular L (one CTA per block).
 int trtri_diag_blocks(cudaStream_t stream, const double* L, int64_t ldl, int n, double* Dinv, int64_t ldd);
@@ -22,19 +16,12 @@ int trtri_diag_blocks(cudaStream_t stream, const double* L, int64_t ldl, int n, 
 int trsm_left_lower(cudaStream_t stream, bool trans, int n, int nrhs, const double* L, int64_t ldl,
                     const double* Dinv, int64_t ldd, double* B, int64_t ldb);
 
-// X <- X L^-T  (solve X L^T = B in place; X is rows x n), used by the Cholesky panel step.
-int trsm_right_lower_t(cudaStream_t stream, int rows, int n, const double* L, int64_t ldl, const double* Dinv,
-                       int64_t ldd, double* X, int64_t ldx);
-
-}  // namespace gpirt
-
-namespace gpirt {
-
 constexpr int CHOL_NB = 128;  // panel width of the right-looking factorisation; diagonal blocks done by one CTA
 
 // Right-looking blocked Cholesky (lower), panel width 128.  Per panel: k_diag128 factorises AND inverts the 128 x 128
 // diagonal block in one CTA; the panel below is multiplied by that inverse and the trailing matrix gets a rank-128
-// update, both on the DMMA GEMM.  Dinv128 (n x 128, ld ldd) receives the inverse of every diagonal block of L.
+// update, both on the DMMA GEMM.  Dinv128 (n x 128, ld ldd) receives the inverse of every diagonal block of L; only the
+// lower triangles are written, so the caller zero-initialises Dinv128 once.
 struct CholLookahead {      // second stream + events for the one-panel look-ahead (owned by the caller)
     cudaStream_t aux = nullptr;
     std::vector<cudaEvent_t> ev_panel, ev_bulk;

@@ -22,7 +22,8 @@
 
 namespace gpirt {
 
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
+std::mutex& device_once_mutex() { static std::mutex mu; return mu; }
 static thread_local char g_last_error[512] = "";
 void set_last_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap); va_end(ap);
@@ -31,15 +32,14 @@ const char* last_error() { return g_last_error; }
 
 int pool_alloc(void** p, size_t bytes, cudaStream_t st) {
     static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    {
+        DeviceOnce once(configured);
+        int dev = 0;
         cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        if (once.first && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t keep = UINT64_MAX;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-        configured[dev] = true;
     }
     cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 256, st);
     if (e != cudaSuccess) {
@@ -100,6 +100,7 @@ struct gpirt_b200_sampler {
     int trsm_bwd(cudaStream_t st);
     int gather_solves(cudaStream_t st);
     bool has_missing = false;
+    int ess_shape = -1, beta_shape = -1;   // ItemShape the last ESS / beta launch picked (gpirt_b200_sampler_uses)
     bool timing = true;
     uint32_t sweep_counter = 0;
     int64_t launches_at_create = 0;
@@ -201,6 +202,17 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         return GPIRT_B200_ERR_ARG;
     }
     if (o) opts = *o;
+    if (opts.world_size > 1) {   // item sharding: every rank can check these without talking to its peers
+        if (opts.rank < 0 || opts.rank >= opts.world_size || opts.world_size > 4096) {
+            set_last_error("bad argument: rank %d of world_size %d", opts.rank, opts.world_size);
+            return GPIRT_B200_ERR_ARG;
+        }
+        if (opts.m_global < opts.world_size || opts.item_offset < 0 || opts.item_offset + m_ > opts.m_global) {
+            set_last_error("bad argument: item block [%lld, %lld) of m_global = %lld on %d ranks (every rank needs at least one item)",
+                           (long long)opts.item_offset, (long long)(opts.item_offset + m_), (long long)opts.m_global, opts.world_size);
+            return GPIRT_B200_ERR_ARG;
+        }
+    }
     n = (int)n_; m = (int)m_;
     ldn = round_up(n, 8); ldN = round_up(N_GRID, 8); ldy8 = round_up(n, 16);
     int ndev = 0;
@@ -232,6 +244,9 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     }
 
     const size_t nm = (size_t)ldn * m, Nm = (size_t)ldN * m;
+    // K* / S^-1 K* hold world x ceil(1001 / world) grid columns: the in-place all-gather of the per-rank slices pads the
+    // last rank's slice to full width
+    const size_t kcols = (size_t)comm.world * (size_t)ceil_div(N_GRID, comm.world) + 8;
     {   // the theta contraction runs on the int8 tensor cores (y is an exact int8 operand); GPIRT_THETA_INT8=0 keeps
         // the FP64 DMMA contraction instead, which needs y as doubles
         const char* e = getenv("GPIRT_THETA_INT8");
@@ -242,15 +257,16 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(theta, (size_t)ldn)); GP_TRY(alloc(theta_star, (size_t)ldN)); GP_TRY(alloc(prior, (size_t)ldN));
     GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
     GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * CHOL_NB));
-    GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * (N_GRID + 8)));
+    GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * kcols));
     GP_TRY(alloc(panel_scratch, (size_t)ldn * CHOL_NB));
     lookahead.panel_scratch = panel_scratch; lookahead.ld_scratch = ldn;
     GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
-    GP_TRY(alloc(kstar, (size_t)ldn * (N_GRID + 8))); GP_TRY(alloc(s, (size_t)ldN));
+    GP_TRY(alloc(kstar, (size_t)ldn * kcols)); GP_TRY(alloc(s, std::max((size_t)ldN, kcols)));
     GP_TRY(alloc(logPt, (size_t)ldN * (n + 1))); GP_TRY(alloc(partial, (size_t)N_CHUNKS * N_GRID));
     GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2)); GP_TRY(alloc(work, 4));
     GP_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int), stream));
+    GP_CUDA(cudaMemsetAsync(Dinv, 0, (size_t)ldn * CHOL_NB * sizeof(double), stream));   // the factorisation writes the lower triangles only
     GP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream));
     GP_CUDA(cudaMemsetAsync(irf_sum, 0, Nm * sizeof(double), stream));
     GP_CUDA(cudaMemsetAsync(y8, 0, (size_t)ldy8 * m, stream));
@@ -363,7 +379,7 @@ int gpirt_b200_sampler::step_draw_f(uint32_t sweep) {
     toc();
     if (sweep == 0) return GPIRT_B200_OK;   // initial f_j = rmvnorm(cholS), gpirtMCMC.cpp:19-21
     tic(GPIRT_B200_T_ESS);
-    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, k, item_offset, nprop, status + 1, work));
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, k, item_offset, nprop, status + 1, work, &ess_shape));
     toc();
     return GPIRT_B200_OK;
 }
@@ -510,7 +526,7 @@ int gpirt_b200_sampler::step_draw_fstar(uint32_t sweep, int accumulate) {
 }
 
 __global__ void k_sub_rowsum(double* logPt, int64_t ld, int N, int n, const double* rowsum) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x, i = blockIdx.x;   // respondents on grid.x (n may exceed 65535)
     if (k < N && i < n) logPt[k + (int64_t)i * ld] -= rowsum[k];
 }
 
@@ -536,7 +552,7 @@ int gpirt_b200_sampler::step_draw_theta(uint32_t sweep) {
     if (comm.world > 1) {
         tic(GPIRT_B200_T_ALLREDUCE);
         if (!has_missing) {
-            dim3 grid((unsigned)ceil_div(N, 256), (unsigned)n);
+            dim3 grid((unsigned)n, (unsigned)ceil_div(N, 256));
             GP_LAUNCH(k_sub_rowsum, grid, 256, 0, stream, logPt, ldN, N, n, rowsum);
         }
         rs_for_draw = nullptr;
@@ -552,7 +568,7 @@ int gpirt_b200_sampler::step_draw_theta(uint32_t sweep) {
 // beta = draw_beta(beta, X, y, f, ...) with X.col(1) = the NEW theta                 gpirtMCMC.cpp:71-73, draw-beta.cpp
 int gpirt_b200_sampler::step_draw_beta(uint32_t sweep) {
     tic(GPIRT_B200_T_BETA);
-    GP_TRY(launch_beta(stream, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1, work + 1));
+    GP_TRY(launch_beta(stream, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1, work + 1, &beta_shape));
     toc();
     return GPIRT_B200_OK;
 }
@@ -569,7 +585,7 @@ int gpirt_b200_sampler::init_draws() {
 // ESS with nu already in place (the product L z was accumulated behind the previous sweep's factorisation)
 int gpirt_b200_sampler::ess_only(uint32_t sweep) {
     tic(GPIRT_B200_T_ESS);
-    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1, work));
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1, work, &ess_shape));
     toc();
     return GPIRT_B200_OK;
 }
@@ -596,7 +612,7 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         Seg sb = tic_on(GPIRT_B200_T_BETA, st_beta);
         // one CTA per item here, not the persistent variant: its CTAs retire every few microseconds, so the chain's short
         // high-priority kernels get SMs (a persistent CTA owns the whole register file of its SM: measured +0.5 ms/sweep)
-        GP_TRY(launch_beta(st_beta, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1, nullptr));
+        GP_TRY(launch_beta(st_beta, beta, f, ldn, y8, ldy8, theta, pm, psd, pstep, n, m, key_at(sweep), item_offset, status + 1, nullptr, &beta_shape));
         toc_on(sb, st_beta);
         GP_CUDA(cudaEventRecord(ev_beta, st_beta));
     }
@@ -731,7 +747,8 @@ struct Bounce {
         return GPIRT_B200_OK;
     }
 };
-Bounce g_bounce;   // process-wide, reused across calls
+Bounce g_bounce;        // process-wide, reused across calls (2 x n*m*8 bytes of pinned memory once f draws are stored)
+std::mutex g_bounce_mu; // one gpirt_b200_mcmc call at a time drains through it (concurrent calls take turns per slice)
 
 int host_threads_for_copy() {
     const char* e = getenv("GPIRT_COPY_THREADS");
@@ -744,6 +761,7 @@ int host_threads_for_copy() {
 
 // dst (pageable host) <- src (device), count doubles, via bounce buffer `b` on `stream`
 int chunked_d2h(double* dst, const double* src, size_t count, int b, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_bounce_mu);
     const size_t chunk = (size_t)4 << 20;   // 4 Mi doubles = 32 MiB
     const int nchunks = (int)((count + chunk - 1) / chunk);
     if (g_bounce.ensure(count) != GPIRT_B200_OK) {   // no pinned memory: plain (driver-staged) copy
@@ -805,7 +823,12 @@ const char* gpirt_b200_strerror(int status) {
 const char* gpirt_b200_last_error(void) { return gpirt::last_error(); }
 
 int gpirt_b200_release_memory(void) {
-    comm_shutdown();
+    GP_TRY(comm_shutdown());
+    {
+        std::lock_guard<std::mutex> lock(g_bounce_mu);
+        for (auto& p : g_bounce.buf) { if (p) cudaFreeHost(p); p = nullptr; }
+        g_bounce.cap = 0;
+    }
     int dev = 0;
     GP_CUDA(cudaGetDevice(&dev));
     cudaMemPool_t pool;
@@ -838,17 +861,17 @@ int gpirt_b200_sampler_init_draws(gpirt_b200_sampler* s) { return s ? s->init_dr
 
 int gpirt_b200_sampler_sweep(gpirt_b200_sampler* s, int n_sweeps, int accumulate_irf, float* elapsed_ms) {
     if (!s || n_sweeps < 0) return GPIRT_B200_ERR_ARG;
-    cudaEvent_t e0, e1;
-    GP_CUDA(cudaEventCreate(&e0)); GP_CUDA(cudaEventCreate(&e1));
-    GP_CUDA(cudaEventRecord(e0, s->stream));
-    int rc = GPIRT_B200_OK;
-    for (int t = 0; t < n_sweeps && rc == GPIRT_B200_OK; ++t) rc = s->sweep(accumulate_irf);
-    GP_CUDA(cudaEventRecord(e1, s->stream));
+    struct Events {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } ev;
+    GP_CUDA(cudaEventCreate(&ev.e0)); GP_CUDA(cudaEventCreate(&ev.e1));
+    GP_CUDA(cudaEventRecord(ev.e0, s->stream));
+    for (int t = 0; t < n_sweeps; ++t) GP_TRY(s->sweep(accumulate_irf));
+    GP_CUDA(cudaEventRecord(ev.e1, s->stream));
     cudaError_t e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) { set_last_error("sweep failed: %s", cudaGetErrorString(e)); rc = GPIRT_B200_ERR_CUDA; }
-    if (elapsed_ms && rc == GPIRT_B200_OK) cudaEventElapsedTime(elapsed_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (rc != GPIRT_B200_OK) return rc;
+    if (e != cudaSuccess) { set_last_error("sweep failed: %s", cudaGetErrorString(e)); return GPIRT_B200_ERR_CUDA; }
+    if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, ev.e0, ev.e1);
     return s->check_status();
 }
 
@@ -954,6 +977,9 @@ int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature) {
     if (!s) return -1;
     if (feature == 0) return s->use_ti8 ? 1 : 0;
     if (feature == 1) return s->use_i8gemm ? 1 : 0;
+    if (feature == 2) return s->ess_shape;
+    if (feature == 3) return s->beta_shape;
+    if (feature == 4) return s->solve_mode;
     return -1;
 }
 
@@ -966,6 +992,26 @@ void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s) {
 // ----------------------------------------------------------------------------------------------------------------------
 // gpirtMCMC(): src/gpirtMCMC.cpp:5-117
 // ----------------------------------------------------------------------------------------------------------------------
+static thread_local int64_t g_last_degenerate_theta = 0;
+int64_t gpirt_b200_last_degenerate_theta(void) { return g_last_degenerate_theta; }
+
+// running mean / sum of squared deviations of f over the sampling iterations (Welford), count = iterations so far incl. this
+__global__ void __launch_bounds__(256) k_f_welford(const double* __restrict__ f, int64_t ld, int n, double count,
+                                                   double* __restrict__ mean, double* __restrict__ m2) {
+    const int i = blockIdx.y * blockDim.x + threadIdx.x, j = blockIdx.x;
+    if (i >= n) return;
+    const int64_t o = i + (int64_t)j * n;
+    const double x = f[i + (int64_t)j * ld];
+    const double mu = (count == 1.0) ? 0.0 : mean[o], q = (count == 1.0) ? 0.0 : m2[o];
+    const double d = x - mu, mu2 = mu + d / count;
+    mean[o] = mu2;
+    m2[o] = fma(d, x - mu2, q);
+}
+__global__ void __launch_bounds__(256) k_f_sd(double* __restrict__ m2, size_t count_elems, double denom) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count_elems) m2[i] = sqrt(m2[i] / denom);   // denom = S - 1 (R's sd); S = 1 gives NaN like sd() of one value
+}
+
 int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_init, int sample_iterations,
                     int burn_iterations, const double* pm, const double* psd, const double* pstep,
                     const gpirt_b200_opts* opts, double* theta_out, double* beta_out, double* f_out, double* irf_out,
@@ -976,8 +1022,14 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     }
     const bool keep_f = !(opts && opts->skip_f_draws);
     if (keep_f && !f_out) { set_last_error("f_out is NULL but f draws were requested"); return GPIRT_B200_ERR_ARG; }
+    if (opts && opts->thin < 0) { set_last_error("bad argument: thin < 0"); return GPIRT_B200_ERR_ARG; }
+    const int thin = (opts && opts->thin > 1) ? opts->thin : 1;
+    double* f_mean_out = opts ? opts->f_mean_out : nullptr;
+    double* f_sd_out = opts ? opts->f_sd_out : nullptr;
+    const bool summarise_f = f_mean_out || f_sd_out;
     const bool trace = getenv("GPIRT_TIMING") != nullptr;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    g_last_degenerate_theta = 0;
     double t_a = now();
     gpirt_b200_sampler* s = nullptr;
     GP_TRY(gpirt_b200_sampler_create(&s, y, n, m, theta_init, pm, psd, pstep, opts));
@@ -987,31 +1039,43 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     // enqueues sweep t+1, and only then blocks in the device-to-host copy of snapshot t on a second stream.
     struct Guard {
         gpirt_b200_sampler* s; cudaStream_t copy; cudaEvent_t ev[2]; double* snap_f[2]; double* snap_small[2];
+        double *f_mean, *f_m2, *agree_dev; int* h_poll;
         ~Guard() {
             if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
             for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); pool_free(snap_f[i], s->stream); pool_free(snap_small[i], s->stream); }
+            pool_free(f_mean, s->stream); pool_free(f_m2, s->stream); pool_free(agree_dev, s->stream);
+            if (h_poll) cudaFreeHost(h_poll);
             gpirt_b200_sampler_destroy(s);
         }
-    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-    const int S1 = sample_iterations + 1;
+    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr};
+    const int n_slots = sample_iterations / thin + 1;         // slot 0 = initial values, slot k = sampling iteration k * thin
     const size_t nm = (size_t)n * m;
     if (keep_f && !getenv("GPIRT_NO_HUGEPAGE_HINT")) {
         // the caller's f array is fresh pageable memory: ask for transparent huge pages on its interior so that the
         // first-touch faults of the draw stores are 2 MiB each instead of 4 KiB (advisory; ignored where THP is off)
         const uintptr_t a = ((uintptr_t)f_out + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
-        const uintptr_t b = ((uintptr_t)f_out + (size_t)S1 * nm * sizeof(double)) & ~(((uintptr_t)2 << 20) - 1);
+        const uintptr_t b = ((uintptr_t)f_out + (size_t)n_slots * nm * sizeof(double)) & ~(((uintptr_t)2 << 20) - 1);
         if (b > a) madvise((void*)a, b - a, MADV_HUGEPAGE);
     }
     std::vector<double> small((size_t)n + 2 * (size_t)m);
     GP_CUDA(cudaStreamCreateWithFlags(&gd.copy, cudaStreamNonBlocking));
+    GP_CUDA(cudaHostAlloc((void**)&gd.h_poll, 4 * sizeof(int) + 8 * sizeof(double), cudaHostAllocDefault));
+    std::memset(gd.h_poll, 0, 4 * sizeof(int) + 8 * sizeof(double));   // [0..3] status words, then a ring of 8 agreed stop flags
+    double* h_ring = reinterpret_cast<double*>(gd.h_poll + 4);
+    int agree_count = 0, agree_at_snapshot[2] = {-1, -1};
     for (int i = 0; i < 2; ++i) {
         GP_CUDA(cudaEventCreateWithFlags(&gd.ev[i], cudaEventDisableTiming));
         GP_TRY(pool_alloc((void**)&gd.snap_small[i], small.size() * sizeof(double), s->stream));
         if (keep_f) GP_TRY(pool_alloc((void**)&gd.snap_f[i], nm * sizeof(double), s->stream));
     }
+    if (summarise_f) {
+        GP_TRY(pool_alloc((void**)&gd.f_mean, nm * sizeof(double), s->stream));
+        GP_TRY(pool_alloc((void**)&gd.f_m2, nm * sizeof(double), s->stream));
+    }
+    const bool sharded = s->comm.world > 1;
+    if (sharded) GP_TRY(pool_alloc((void**)&gd.agree_dev, sizeof(double), s->stream));
     double t_c = now();
-    int rc = s->init_draws();
-    if (rc) return rc;
+    GP_TRY(s->init_draws());
     double t_d = now(), t_store = 0.0;
     // snapshot(slot): main stream copies theta | beta (and f, tightly packed) into buffer slot & 1 and records the event
     auto snapshot = [&](int slot) -> int {
@@ -1022,46 +1086,115 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
             GP_CUDA(cudaMemcpy2DAsync(gd.snap_f[b], (size_t)n * sizeof(double), s->f, s->ldn * sizeof(double), (size_t)n * sizeof(double),
                                       (size_t)m, cudaMemcpyDeviceToDevice, s->stream));
         GP_CUDA(cudaEventRecord(gd.ev[b], s->stream));
+        agree_at_snapshot[b] = agree_count - 1;   // the newest agreement this snapshot's event covers
         return GPIRT_B200_OK;
     };
-    // drain(slot): copy stream waits for the snapshot, then the host blocks in the device-to-host copies
+    // drain(slot): copy stream waits for the snapshot, then the host blocks in the device-to-host copies.  The sampler's
+    // status words (Cholesky / ESS failure) ride along, so a failed chain stops at the next stored slot instead of
+    // spinning every item through the ESS iteration cap for the rest of the run.
     auto drain = [&](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
         const double ts0 = now();
         const int b = slot & 1;
         GP_CUDA(cudaStreamWaitEvent(gd.copy, gd.ev[b], 0));
+        GP_CUDA(cudaMemcpyAsync(gd.h_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, gd.copy));
         GP_CUDA(cudaMemcpyAsync(small.data(), gd.snap_small[b], small.size() * sizeof(double), cudaMemcpyDeviceToHost, gd.copy));
         if (keep_f) GP_TRY(chunked_d2h(f_out + (size_t)slot * nm, gd.snap_f[b], nm, b, gd.copy));
         GP_CUDA(cudaStreamSynchronize(gd.copy));
-        for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * S1 + slot] = small[i];
+        for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * n_slots + slot] = small[i];
         std::memcpy(beta_out + (size_t)slot * 2 * m, small.data() + n, 2 * (size_t)m * sizeof(double));
         t_store += now() - ts0;
         return GPIRT_B200_OK;
+    };
+    // Stopping early (interrupt from the progress callback, failed Cholesky / ESS seen in the polled status words) must be
+    // a COMMON decision when items are sharded: a rank that returned alone would leave its peers blocked in the next
+    // sweep's collectives.  Every rank therefore enqueues, at the same points of the iteration sequence, a one-word
+    // all-reduce of its local stop request on the sampler's stream and acts on the agreed value of a GIVEN agreement (ring
+    // slot) at the host sync that covers it — the same program point on every rank.
+    bool want_stop = false;
+    int stop_code = GPIRT_B200_OK;
+    auto local_stop_code = [&]() -> int {
+        if (gd.h_poll[0]) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
+        if (gd.h_poll[1]) { set_last_error("elliptical slice sampler did not terminate (NaN log-likelihood?)"); return GPIRT_B200_ERR_ESS; }
+        if (want_stop) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
+        return GPIRT_B200_OK;
+    };
+    auto enqueue_agreement = [&]() -> int {
+        if (!sharded) return GPIRT_B200_OK;
+        const double mine = (want_stop || gd.h_poll[0] || gd.h_poll[1]) ? 1.0 : 0.0;   // pageable source: staged at call time
+        GP_CUDA(cudaMemcpyAsync(gd.agree_dev, &mine, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        GP_TRY(comm_allreduce_sum_f64(s->comm, gd.agree_dev, 1, s->stream));
+        GP_CUDA(cudaMemcpyAsync(h_ring + (agree_count & 7), gd.agree_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        agree_count += 1;
+        return GPIRT_B200_OK;
+    };
+    auto stop_now = [&](int agreement) -> bool {   // after a host sync that covers agreement number `agreement`
+        stop_code = local_stop_code();
+        if (sharded) {
+            if (agreement < 0 || h_ring[agreement & 7] == 0.0) return false;
+            if (stop_code == GPIRT_B200_OK) { set_last_error("stopped: another rank was interrupted or failed"); stop_code = GPIRT_B200_ERR_INTERRUPT; }
+            return true;
+        }
+        return stop_code != GPIRT_B200_OK;
     };
     GP_TRY(snapshot(0));                                                            // :53-55 initial values
     int pending = 0;                                                                // slot whose snapshot is not drained yet
     const int total = sample_iterations + burn_iterations;
     const double inc = total > 0 ? 100.0 / total : 0.0;
     double progress = 0.0;
+    int n_summarised = 0;
     for (int iter = 0; iter < total; ++iter) {
-        if (cb && cb(progress, cb_ctx)) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
+        if (cb && cb(progress, cb_ctx)) want_stop = true;                           // Rcpp::checkUserInterrupt, :66,85
+        if (want_stop && !sharded) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
         progress += inc;
         const bool sampling = iter >= burn_iterations;
+        const int si = iter - burn_iterations + 1;                                  // 1-based sampling iteration
+        const bool store = sampling && si % thin == 0;
         GP_TRY(s->sweep(sampling ? 1 : 0));                                         // enqueue sweep (asynchronous)
-        if (pending >= 0) { GP_TRY(drain(pending)); pending = -1; }                 // previous slot goes out while it runs
-        else if ((iter & 7) == 7) GP_CUDA(cudaStreamSynchronize(s->stream));         // keep progress / interrupts honest in burn-in
-        if (sampling) {
-            const int slot = iter - burn_iterations + 1;                            // :99-103
+        if (sampling && summarise_f) {
+            dim3 grid((unsigned)m, (unsigned)ceil_div(n, 256));
+            GP_LAUNCH(k_f_welford, grid, 256, 0, s->stream, s->f, s->ldn, (int)n, (double)(++n_summarised), gd.f_mean, gd.f_m2);
+        }
+        const bool sync_point = store || (iter & 7) == 7;
+        if (sync_point) GP_TRY(enqueue_agreement());
+        if (pending >= 0) {                                                         // previous slot goes out while the sweep runs
+            const int covered = agree_at_snapshot[pending & 1];
+            GP_TRY(drain(pending));
+            pending = -1;
+            if (stop_now(covered)) return stop_code;
+        } else if ((iter & 7) == 7) {                                               // keep progress / interrupts honest between stores
+            GP_CUDA(cudaMemcpyAsync(gd.h_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            GP_CUDA(cudaStreamSynchronize(s->stream));
+            if (stop_now(agree_count - 1)) return stop_code;
+        }
+        if (store) {
+            const int slot = si / thin;                                             // :99-103
             GP_TRY(snapshot(slot));
             pending = slot;
         }
     }
     if (pending >= 0) GP_TRY(drain(pending));
     GP_CUDA(cudaStreamSynchronize(s->stream));
+    if (stop_now(agree_count - 1)) return stop_code;
     GP_TRY(s->check_status());
+    {
+        int h[4] = {0, 0, 0, 0};
+        GP_CUDA(cudaMemcpy(h, s->status, sizeof(h), cudaMemcpyDeviceToHost));
+        g_last_degenerate_theta = h[2];   // theta draws whose CDF was degenerate (grid point 0 taken; the reference reads out of bounds there)
+    }
     // IRFs = plogis(IRFs / S)   (:106-111; S = 0 gives NaN exactly as the reference's 0 * inf)
     const double inv = 1.0 / (double)sample_iterations;
     GP_TRY(launch_irf_finish(s->stream, s->irf_sum, s->ldN, N_GRID, (int)m, inv, s->Dmat));
     GP_CUDA(cudaMemcpyAsync(irf_out, s->Dmat, (size_t)N_GRID * m * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (summarise_f) {
+        if (n_summarised == 0) {
+            GP_CUDA(cudaMemsetAsync(gd.f_mean, 0xff, nm * sizeof(double), s->stream));   // all-ones bit pattern = NaN: no sampling iterations
+            GP_CUDA(cudaMemsetAsync(gd.f_m2, 0xff, nm * sizeof(double), s->stream));
+        } else {
+            GP_LAUNCH(k_f_sd, (unsigned)ceil_div((int64_t)nm, 256), 256, 0, s->stream, gd.f_m2, nm, (double)(n_summarised - 1));
+        }
+        if (f_mean_out) GP_CUDA(cudaMemcpyAsync(f_mean_out, gd.f_mean, nm * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        if (f_sd_out) GP_CUDA(cudaMemcpyAsync(f_sd_out, gd.f_m2, nm * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
     GP_CUDA(cudaStreamSynchronize(s->stream));
     if (cb) cb(100.0, cb_ctx);
     if (trace)

@@ -22,13 +22,15 @@ def _F(a, shape=None):
 
 
 def make_opts(seed=0, device=-1, fstar_mode=0, skip_f_draws=False, rank=0, world_size=1, m_global=0, item_offset=0,
-              nccl_unique_id=None):
+              nccl_unique_id=None, thin=1, use_graph=0):
     o = Opts()
     o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     o.device = device
     o.fstar_mode = fstar_mode
     o.skip_f_draws = int(bool(skip_f_draws))
     o.rank, o.world_size, o.m_global, o.item_offset = rank, world_size, m_global, item_offset
+    o.thin = int(thin)
+    o.use_graph = int(use_graph)
     o._uid_keepalive = None
     if nccl_unique_id is not None:
         buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
@@ -45,11 +47,13 @@ def nccl_unique_id():
 
 def gpirtMCMC(data, sample_iterations, burn_iterations, vote_codes=None, beta_prior_means=None, beta_prior_sds=None,
               beta_proposal_sds=None, theta_init=None, *, seed=None, progress=None, store_f=True, fstar_mode=0,
-              device=-1, shard=None):
+              device=-1, shard=None, thin=1, f_summary=False, use_graph=0):
     """Drop-in for the reference's gpirtMCMC().  Keyword-only extras (not in the reference): seed (Philox key; default
     drawn from numpy's global RNG, as the R shim draws it from R's), progress(percent) -> truthy to interrupt,
     store_f=False to skip the n*m*(S+1) f draws, shard=(rank, world, m_global, item_offset, unique_id) for item
-    sharding across GPUs."""
+    sharding across GPUs, thin=k to keep every k-th sampling iteration only (outputs then hold 1 + S // k slots; IRFs
+    still average over all S), f_summary=True to also return the posterior mean / sd of f over all sampling iterations
+    (accumulated on the device: "f_mean", "f_sd", n x m)."""
     L = _lib.load()
     y = as_response_matrix(data, vote_codes or DEFAULT_CODES)                        # R/gpirtMCMC.R:93
     y = np.asfortranarray(np.asarray(y, dtype=np.float64))
@@ -68,11 +72,19 @@ def gpirtMCMC(data, sample_iterations, burn_iterations, vote_codes=None, beta_pr
     kw = {}
     if shard is not None:
         kw = dict(rank=shard[0], world_size=shard[1], m_global=shard[2], item_offset=shard[3], nccl_unique_id=shard[4])
-    opts = make_opts(seed=seed, device=device, fstar_mode=fstar_mode, skip_f_draws=not store_f, **kw)
-    theta = np.empty((S + 1, n), order="F")
-    beta = np.empty((2, m, S + 1), order="F")
-    f = np.empty((n, m, S + 1), order="F") if store_f else None
+    thin = int(thin)
+    if thin < 1:
+        raise ValueError("thin must be >= 1")
+    opts = make_opts(seed=seed, device=device, fstar_mode=fstar_mode, skip_f_draws=not store_f, thin=thin, use_graph=use_graph, **kw)
+    slots = S // thin + 1
+    theta = np.empty((slots, n), order="F")
+    beta = np.empty((2, m, slots), order="F")
+    f = np.empty((n, m, slots), order="F") if store_f else None
     irf = np.empty((N_GRID, m), order="F")
+    f_mean = f_sd = None
+    if f_summary:
+        f_mean = np.empty((n, m), order="F"); f_sd = np.empty((n, m), order="F")
+        opts.f_mean_out = _lib.ptr(f_mean); opts.f_sd_out = _lib.ptr(f_sd)
 
     def _cb(pct, _ctx):
         try:
@@ -86,6 +98,8 @@ def gpirtMCMC(data, sample_iterations, burn_iterations, vote_codes=None, beta_pr
     out = dict(theta=theta, beta=beta, IRFs=irf)
     if store_f:
         out["f"] = f
+    if f_summary:
+        out["f_mean"], out["f_sd"] = f_mean, f_sd
     return out
 
 

@@ -9,9 +9,9 @@ import numpy as np
 
 
 def item_block(m, rank, world):
-    """[j0, j1) of the contiguous item block owned by `rank` (the last blocks may be shorter or empty)."""
-    per = (m + world - 1) // world
-    return min(m, rank * per), min(m, (rank + 1) * per)
+    """[j0, j1) of the contiguous item block owned by `rank`: balanced blocks (sizes differ by at most one), so no rank is
+    left without items as long as m >= world (the library rejects m_global < world_size on every rank)."""
+    return (rank * m) // world, ((rank + 1) * m) // world
 
 
 def share_unique_id(dist, rank, make_uid, device=None):

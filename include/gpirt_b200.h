@@ -46,6 +46,13 @@ typedef struct gpirt_b200_opts {
     int64_t item_offset;  /* global index of this rank's first item (y, priors and outputs are the LOCAL block) */
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (rank 0: gpirt_b200_nccl_unique_id);
                                    NULL on a later call re-uses the communicator the previous call created */
+    /* draw storage (src/gpirtMCMC.cpp:49-55,99-103 stores every sampling iteration: n*m*8 bytes of f each) */
+    int32_t thin;         /* > 1: keep the draws of every thin-th sampling iteration only; theta_out / beta_out / f_out then
+                             hold 1 + sample_iterations / thin slots (slot 0 = initial values, slot k = sampling iteration
+                             k * thin).  IRFs still average over ALL sampling iterations.  0 or 1: the reference's contract */
+    int32_t reserved0;
+    double* f_mean_out;   /* optional n x m: posterior mean of f over all sampling iterations, accumulated on the device */
+    double* f_sd_out;     /* optional n x m: posterior standard deviation of f (denominator S - 1, as R's sd()) */
 } gpirt_b200_opts;
 
 /* Progress / interrupt callback: called once per iteration with percent complete (as the reference's Rprintf,
@@ -68,6 +75,10 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
 
 const char* gpirt_b200_strerror(int status);
 const char* gpirt_b200_last_error(void); /* detail of the last failure on this thread (CUDA / NCCL message) */
+/* number of theta draws of the last gpirt_b200_mcmc() call on this thread whose grid CDF was degenerate (all mass on grid
+ * point 0 after max-subtraction): the sampler takes grid point 0 there, the reference reads theta_star[1001] out of bounds
+ * (src/draw-theta.cpp:28-33).  0 in every healthy run; the R shim turns a non-zero count into a warning. */
+int64_t gpirt_b200_last_degenerate_theta(void);
 int gpirt_b200_device_count(void);
 /* device memory and the NCCL communicator are kept across calls (a second gpirtMCMC() re-uses them); this releases them */
 int gpirt_b200_release_memory(void);
@@ -127,8 +138,11 @@ int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled); /* per-st
  * Z fill and L Z product (identical draws either way; off gives un-overlapped per-kernel timings) */
 int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled);
 int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s); /* kernels launched by this sampler so far */
-/* which tensor-core path this sampler selected: feature 0 = int8 theta contraction, 1 = fixed-point (int8) L Z / f* /
- * K*-solve products; returns 1 / 0, or -1 for an unknown feature (bench.py picks the roofline denominator by it) */
+/* which code path this sampler selected (bench.py picks the roofline denominator by it, the parity tests assert it):
+ * feature 0 = int8 theta contraction (1/0), 1 = fixed-point (int8) L Z / f* / K*-solve products (1/0),
+ * 2 / 3 = launch shape of the last ESS / beta step (0 one CTA per item, 1 persistent CTAs, 2 streaming shape for
+ * n > 4096; -1 before the first launch), 4 = K*-solve route (0 through L^-1, 1 blocked substitution);
+ * -1 for an unknown feature */
 int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature);
 void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s);
 

@@ -124,6 +124,11 @@ void* gpo_rng_tape(const double* vals, const uint8_t* kinds, size_t len) {
 }
 void gpo_rng_free(void* h) { delete (Rng*)h; }
 void gpo_rng_set_sweep(void* h, uint32_t sweep) { ((Rng*)h)->sweep = sweep; }
+/* which = 0: item streams, 1: respondent streams; len = 0 clears the map (gpo_rng.h) */
+void gpo_rng_set_stream_map(void* h, int which, const uint32_t* map, size_t len) {
+    std::vector<uint32_t>& m = which ? ((Rng*)h)->resp_map : ((Rng*)h)->item_map;
+    m.assign(map, map + len);
+}
 size_t gpo_rng_tape_len(void* h) { return ((Rng*)h)->tape_val.size(); }
 size_t gpo_rng_tape_pos(void* h) { return ((Rng*)h)->pos; }
 int gpo_rng_error(void* h) { return ((Rng*)h)->error; }

@@ -81,15 +81,25 @@ struct Rng {
     std::vector<uint8_t> tape_kind;
     size_t pos = 0;
     int error = 0; /* 1 = tape exhausted, 2 = kind mismatch */
+    /* Optional stream maps (keyed mode): a step function run on a SUBSET of items / respondents addresses its variates
+     * with the GLOBAL indices of the subset, stream = map[local index] — how the parity tests check sampled items and
+     * respondents of a full-size problem against the sampler, whose streams are global indices. */
+    std::vector<uint32_t> item_map, resp_map;
+    uint32_t map_stream(uint32_t purpose, uint32_t stream) const {
+        const std::vector<uint32_t>& m = (purpose == P_THETA_U) ? resp_map : item_map;
+        return (!m.empty() && stream < m.size()) ? m[stream] : stream;
+    }
 
     double norm(uint32_t purpose, uint32_t stream, uint32_t idx) {
         if (kind == TAPE) return pop('n');
+        stream = map_stream(purpose, stream);
         double v = keyed_normal(seed, sweep, purpose, stream, idx);
         if (record) { tape_val.push_back(v); tape_kind.push_back('n'); }
         return v;
     }
     double unif(uint32_t purpose, uint32_t stream, uint32_t idx) {
         if (kind == TAPE) return pop('u');
+        stream = map_stream(purpose, stream);
         double v = keyed_uniform(seed, sweep, purpose, stream, idx);
         if (record) { tape_val.push_back(v); tape_kind.push_back('u'); }
         return v;

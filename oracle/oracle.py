@@ -57,6 +57,7 @@ def lib():
         L.gpo_rng_tape.argtypes = [_dp, _bp, C.c_size_t]
         L.gpo_rng_free.argtypes = [C.c_void_p]
         L.gpo_rng_set_sweep.argtypes = [C.c_void_p, C.c_uint32]
+        L.gpo_rng_set_stream_map.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_size_t]
         L.gpo_rng_tape_len.restype = C.c_size_t
         L.gpo_rng_tape_len.argtypes = [C.c_void_p]
         L.gpo_rng_tape_pos.restype = C.c_size_t
@@ -96,6 +97,18 @@ class Rng:
 
     def set_sweep(self, sweep):
         lib().gpo_rng_set_sweep(self.h, sweep)
+
+    def set_item_map(self, items):
+        """local item index j of the following calls draws from stream items[j] (global item index); None clears"""
+        self._set_map(0, items)
+
+    def set_respondent_map(self, rows):
+        """local respondent index i of the following draw_theta calls draws from stream rows[i]; None clears"""
+        self._set_map(1, rows)
+
+    def _set_map(self, which, idx):
+        a = np.ascontiguousarray([] if idx is None else idx, dtype=np.uint32)
+        lib().gpo_rng_set_stream_map(self.h, which, a.ctypes.data_as(C.POINTER(C.c_uint32)), a.size)
 
     def recorded(self):
         n = lib().gpo_rng_tape_len(self.h)

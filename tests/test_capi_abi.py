@@ -52,7 +52,19 @@ def test_product_package_never_touches_the_oracle():
                     "%s mentions the oracle" % os.path.join(dirpath, f)
 
 
-def test_opts_struct_layout_matches_header():
+def test_opts_struct_layout_matches_header(tmp_path):
+    """the ctypes mirror of gpirt_b200_opts against offsetof() of the real header, compiled with the C compiler"""
+    import subprocess
     from gpirt_b200._lib import Opts
-    assert C.sizeof(Opts) == 8 + 4 * 6 + 8 + 8 + 8
-    assert Opts.seed.offset == 0 and Opts.rank.offset == 24 and Opts.m_global.offset == 32 and Opts.nccl_unique_id.offset == 48
+    fields = [name for name, _ in Opts._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gpirt_b200.h"\nint main(void) {\n'
+                   + "".join('  printf("%s %%zu\\n", offsetof(gpirt_b200_opts, %s));\n' % (f, f) for f in fields)
+                   + '  printf("sizeof %zu\\n", sizeof(gpirt_b200_opts));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for f in fields:
+        assert int(got[f]) == getattr(Opts, f).offset, f
+    assert int(got["sizeof"]) == C.sizeof(Opts)
+    assert Opts.seed.offset == 0 and Opts.rank.offset == 24 and Opts.nccl_unique_id.offset == 48   # round-1 prefix unchanged
