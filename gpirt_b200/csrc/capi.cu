@@ -104,7 +104,9 @@ int gpirt_b200_chol_lower(double* S, int64_t n) {
     GP_CUDA(cudaMemset(st, 0, sizeof(double)));
     GP_CUDA(cudaMemset(dinv.p, 0, (size_t)ld * CHOL_NB * sizeof(double)));   // potrf_lower_rl writes the lower triangles only
     GP_TRY(h2d(a.p, ld, S, n, n, n));
-    int rc = potrf_lower_rl(0, a.p, ld, (int)n, dinv.p, ld, st);
+    DevBuf flags;   // one counter per panel step (ints; the buffer is sized in doubles)
+    GP_TRY(flags.alloc((size_t)ceil_div(n, CHOL_NB) / 2 + 2));
+    int rc = potrf_lower_rl(0, a.p, ld, (int)n, dinv.p, ld, st, reinterpret_cast<int*>(flags.p));
     int h = 0;
     if (rc == GPIRT_B200_OK && cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GPIRT_B200_ERR_CUDA;
     if (rc) return rc;

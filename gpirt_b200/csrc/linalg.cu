@@ -7,6 +7,7 @@
 // solves never substitute element-wise: the base case multiplies by the stored inverse of a diagonal block (the approach
 // of blocked GPU TRSMs), which is again a GEMM.
 #include "chol_diag.cuh"
+#include "chol_panel.cuh"
 #include "gemm_f64.cuh"
 #include "linalg.cuh"
 
@@ -118,19 +119,47 @@ int trsm_left_lower(cudaStream_t stream, bool trans, int n, int nrhs, const doub
 }
 
 // Right-looking Cholesky with one-panel look-ahead on two streams.
-//   main stream (critical path):  diag(k) -> panel(k) -> [wait bulk(k-1)] -> crit(k) -> diag(k+1) ...
-//   aux stream  (bulk work)     :  [wait panel(k)] -> bulk(k)
-// crit(k) is the rank-128 update of block column k+1 only, bulk(k) that of the remaining trailing matrix (columns
-// >= k+2); the serial diagonal-block kernels therefore overlap the large symmetric updates.
-int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv, int64_t ldd, int* d_status,
-                   CholLookahead* la) {
-    if (n <= 0) return GPIRT_B200_OK;
-    constexpr size_t smem = diag::SMEM_BYTES;
+//   main stream (critical path):  diag(k) -> [wait head of bulk(k-1)] -> panel+update(k) -> diag(k+1) ...
+//   aux stream  (bulk work)     :  [wait panel+update(k)] -> bulk(k) = head (block column k+2), then the rest
+// panel+update(k) (chol_panel.cuh) turns the panel below diagonal block k into L and applies its rank-128 update to
+// block column k+1 only; bulk(k) is the update of the remaining trailing matrix (columns >= k+2).  The critical path
+// only ever waits for the one block column of a bulk update it is about to overwrite, so the serial diagonal-block
+// kernels overlap the large symmetric updates and the aux stream may run up to a whole bulk update behind.
+template <int R>
+static int launch_panel_update(cudaStream_t stream, double* A, int64_t lda, int n, int k0, const double* Dinv, int64_t ldd,
+                               int* counter) {
+    constexpr size_t smem = sizeof(panel::Smem<R>);
     static bool configured[64] = {false};
     {
         DeviceOnce once(configured);
-        if (once.first) GP_CUDA(cudaFuncSetAttribute(diag::k_diag128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (once.first) GP_CUDA(cudaFuncSetAttribute(panel::k_panel_update<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    const int rem = n - k0 - CHOL_NB;
+    GP_LAUNCH(panel::k_panel_update<R>, (unsigned)ceil_div(rem, R), panel::PTHREADS, smem, stream, A, lda, n, k0, Dinv, ldd, counter);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv, int64_t ldd, int* d_status,
+                   int* d_flags, CholLookahead* la) {
+    if (n <= 0) return GPIRT_B200_OK;
+    if ((ldd & 1) || (reinterpret_cast<uintptr_t>(Dinv) & 15)) {
+        set_last_error("potrf_lower_rl: the block-inverse buffer must be 16-byte aligned with an even leading dimension");
+        return GPIRT_B200_ERR_ARG;
+    }
+    constexpr size_t smem = diag::SMEM_BYTES;
+    static bool configured[64] = {false};
+    static int sm_count[64] = {0};
+    int dev = 0;
+    GP_CUDA(cudaGetDevice(&dev));
+    {
+        DeviceOnce once(configured);
+        if (once.first) {
+            GP_CUDA(cudaFuncSetAttribute(diag::k_diag128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) GP_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        }
+    }
+    const int sms = (dev >= 0 && dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
     const int nblk = (int)ceil_div(n, CHOL_NB);
     const bool two = la && la->aux && nblk > 2;
     if (two) {
@@ -141,6 +170,7 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
             la->ev_panel.push_back(e1); la->ev_bulk.push_back(e2);
         }
     }
+    GP_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)nblk * sizeof(int), stream));   // one P_top counter per panel step
     int last_bulk = -1;
     for (int k = 0; k < nblk; ++k) {
         const int k0 = k * CHOL_NB;
@@ -156,46 +186,47 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
             }
             break;
         }
-        double* P = Akk + nb;  // rem x nb panel below the diagonal block
-        GemmArgs g;            // P <- P Dinv_k^T
-        g.M = rem; g.N = nb; g.K = nb; g.A = P; g.lda = lda; g.B = Dinv + k0; g.ldb = ldd; g.C = P; g.ldc = lda;
-        if (la && la->panel_scratch) {
-            // the panel step sits on the critical path: read the source from a scratch copy so the product can use
-            // the small tiles (4x the CTAs of the one-tile-wide in-place form, which must keep N in a single tile)
-            GP_CUDA(cudaMemcpy2DAsync(la->panel_scratch, (size_t)la->ld_scratch * sizeof(double), P, (size_t)lda * sizeof(double),
-                                      (size_t)rem * sizeof(double), (size_t)nb, cudaMemcpyDeviceToDevice, stream));
-            g.A = la->panel_scratch; g.lda = la->ld_scratch;
-        } else {
-            g.force_big = 1;   // in place: one 128-wide column tile, each CTA rewrites only rows it read
-        }
-        GP_TRY(gemm_f64(stream, false, true, g));
-        double* A22 = Akk + (int64_t)nb * (lda + 1);
+        // bulk(k-1) also wrote block column k+1, which panel+update(k) rewrites: only that block column of bulk(k-1) is
+        // waited for (it is the first thing bulk(k-1) does), the rest of bulk(k-1) keeps running on the aux stream
+        if (two && last_bulk >= 0) GP_CUDA(cudaStreamWaitEvent(stream, la->ev_bulk[last_bulk], 0));
+        // 16 rows per CTA as soon as that still fits one wave of CTAs (shorter critical path), else 32
+        if (ceil_div(rem, 16) <= sms) GP_TRY(launch_panel_update<16>(stream, A, lda, n, k0, Dinv + k0, ldd, d_flags + k));
+        else GP_TRY(launch_panel_update<32>(stream, A, lda, n, k0, Dinv + k0, ldd, d_flags + k));
+        const int nb1 = min(CHOL_NB, rem);            // width of block column k+1
+        const int m2 = rem - nb1;                     // order of the trailing matrix from block column k+2 on
+        const int nb2 = min(CHOL_NB, m2);             // width of block column k+2
+        double* P2 = Akk + nb + nb1;                  // rows of the panel from block row k+2 on
+        double* A22 = Akk + (int64_t)(nb + nb1) * (lda + 1);
+        GemmArgs head, rest;                          // bulk(k) = update of block column k+2, then of columns >= k+3 (lower triangle)
+        head.M = m2; head.N = nb2; head.K = nb; head.A = P2; head.lda = lda; head.B = P2; head.ldb = lda;
+        head.C = A22; head.ldc = lda; head.alpha = -1.0; head.beta = 1.0; head.tri = TRI_C_LOWER;
+        rest = head;
+        rest.M = rest.N = m2 - nb2; rest.A = rest.B = P2 + nb2; rest.C = A22 + (int64_t)nb2 * (lda + 1);
         if (!two) {
-            GemmArgs u;        // A22 -= P P^T (lower triangle)
-            u.M = rem; u.N = rem; u.K = nb; u.A = P; u.lda = lda; u.B = P; u.ldb = lda;
-            u.C = A22; u.ldc = lda; u.alpha = -1.0; u.beta = 1.0; u.tri = TRI_C_LOWER;
-            GP_TRY(gemm_f64(stream, false, true, u));
+            if (m2 > 0) GP_TRY(gemm_f64(stream, false, true, head));
+            if (m2 - nb2 > 0) GP_TRY(gemm_f64(stream, false, true, rest));
             continue;
         }
-        const int nb1 = min(CHOL_NB, rem);   // width of block column k+1
         GP_CUDA(cudaEventRecord(la->ev_panel[k], stream));
         if (la->after_panel) GP_TRY(la->after_panel(k, nblk, la->ev_panel[k]));
-        if (rem - nb1 > 0) {                 // bulk(k): columns >= k+2, on the aux stream
+        last_bulk = -1;
+        if (m2 > 0) {
             GP_CUDA(cudaStreamWaitEvent(la->aux, la->ev_panel[k], 0));
-            GemmArgs u;
-            u.M = rem - nb1; u.N = rem - nb1; u.K = nb; u.A = P + nb1; u.lda = lda; u.B = P + nb1; u.ldb = lda;
-            u.C = A22 + (int64_t)nb1 * (lda + 1); u.ldc = lda; u.alpha = -1.0; u.beta = 1.0; u.tri = TRI_C_LOWER;
-            GP_TRY(gemm_f64(la->aux, false, true, u));
-            GP_CUDA(cudaEventRecord(la->ev_bulk[k], la->aux));
+            GP_TRY(gemm_f64(la->aux, false, true, head));
+            GP_CUDA(cudaEventRecord(la->ev_bulk[k], la->aux));   // block column k+2 is up to date with panels <= k
+            last_bulk = k;
+            if (m2 - nb2 > 0) GP_TRY(gemm_f64(la->aux, false, true, rest));
         }
-        if (last_bulk >= 0) GP_CUDA(cudaStreamWaitEvent(stream, la->ev_bulk[last_bulk], 0));   // bulk(k-1) also wrote column k+1
-        last_bulk = (rem - nb1 > 0) ? k : -1;
-        GemmArgs c;            // crit(k): block column k+1
-        c.M = rem; c.N = nb1; c.K = nb; c.A = P; c.lda = lda; c.B = P; c.ldb = lda;
-        c.C = A22; c.ldc = lda; c.alpha = -1.0; c.beta = 1.0; c.tri = TRI_C_LOWER;
-        GP_TRY(gemm_f64(stream, false, true, c));
     }
-    if (two && last_bulk >= 0) GP_CUDA(cudaStreamWaitEvent(stream, la->ev_bulk[last_bulk], 0));
+    if (two) {   // join the aux stream (its last launches follow the last recorded ev_bulk)
+        if ((int)la->ev_bulk.size() <= nblk) {
+            cudaEvent_t e;
+            GP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            la->ev_bulk.push_back(e);
+        }
+        GP_CUDA(cudaEventRecord(la->ev_bulk.back(), la->aux));
+        GP_CUDA(cudaStreamWaitEvent(stream, la->ev_bulk.back(), 0));
+    }
     return GPIRT_B200_OK;
 }
 

@@ -18,21 +18,20 @@ int trsm_left_lower(cudaStream_t stream, bool trans, int n, int nrhs, const doub
 
 constexpr int CHOL_NB = 128;  // panel width of the right-looking factorisation; diagonal blocks done by one CTA
 
-// Right-looking blocked Cholesky (lower), panel width 128.  Per panel: k_diag128 factorises AND inverts the 128 x 128
-// diagonal block in one CTA; the panel below is multiplied by that inverse and the trailing matrix gets a rank-128
-// update, both on the DMMA GEMM.  Dinv128 (n x 128, ld ldd) receives the inverse of every diagonal block of L; only the
-// lower triangles are written, so the caller zero-initialises Dinv128 once.
+// Right-looking blocked Cholesky (lower), panel width 128.  Per panel: k_diag128 (chol_diag.cuh) factorises AND inverts
+// the 128 x 128 diagonal block in one CTA; k_panel_update (chol_panel.cuh) multiplies the panel below by that inverse and
+// applies its rank-128 update to the next block column; the rest of the trailing matrix is updated on the DMMA GEMM.
+// Dinv128 (n x 128, ld ldd, 16-byte aligned, ldd even) receives the inverse of every diagonal block of L; only the lower
+// triangles are written, so the caller zero-initialises Dinv128 once.  d_flags: scratch, ceil(n / 128) ints.
 struct CholLookahead {      // second stream + events for the one-panel look-ahead (owned by the caller)
     cudaStream_t aux = nullptr;
     std::vector<cudaEvent_t> ev_panel, ev_bulk;
     // optional hook: called on the host right after block column k of L has been enqueued as final (event `done`,
     // recorded on the main stream) — lets the caller start work that consumes finished columns while the chain runs
     std::function<int(int k, int nblk, cudaEvent_t done)> after_panel;
-    double* panel_scratch = nullptr;   // optional n x 128 buffer (ld_scratch): lets the panel product leave the in-place form
-    int64_t ld_scratch = 0;
 };
 int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* Dinv128, int64_t ldd, int* d_status,
-                   CholLookahead* la = nullptr);
+                   int* d_flags, CholLookahead* la = nullptr);
 
 // X = L^-1 (n x n, lower; strict upper zero) by batched recursive doubling from the 128 x 128 block inverses:
 //   inv([[L11,0],[L21,L22]]) = [[X11,0],[-X22 L21 X11, X22]], all pairs of one level in a single batched GEMM launch.

@@ -109,8 +109,9 @@ struct gpirt_b200_sampler {
     double *yd = nullptr, *theta = nullptr, *theta_star = nullptr, *prior = nullptr, *beta = nullptr, *pm = nullptr,
            *psd = nullptr, *pstep = nullptr, *L = nullptr, *Dinv = nullptr, *f = nullptr, *Z = nullptr, *nu = nullptr,
            *fstar = nullptr, *Dmat = nullptr, *irf_sum = nullptr, *kstar = nullptr, *s = nullptr, *logPt = nullptr,
-           *partial = nullptr, *Linv = nullptr, *Tmp = nullptr, *kstar2 = nullptr, *panel_scratch = nullptr;
+           *partial = nullptr, *Linv = nullptr, *Tmp = nullptr, *kstar2 = nullptr;
     int* work = nullptr;   // item counters of the persistent per-item kernels: [0] ESS, [1] beta
+    int* chol_flags = nullptr;   // scratch of the factorisation: one counter per panel step
     int *nprop = nullptr, *theta_idx = nullptr, *status = nullptr;  // status[0] chol, [1] ess, [2] theta-degenerate count
     unsigned long long* counters = nullptr;                        // [0] missing cells, [1] illegal cells
     static constexpr int N_CHUNKS = 128;   // item chunks of the D row sums: enough CTAs to cover the HBM latency of the column walk
@@ -258,8 +259,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(beta, 2 * (size_t)m)); GP_TRY(alloc(pm, 2 * (size_t)m)); GP_TRY(alloc(psd, 2 * (size_t)m)); GP_TRY(alloc(pstep, 2 * (size_t)m));
     GP_TRY(alloc(L, (size_t)ldn * n)); GP_TRY(alloc(Dinv, (size_t)ldn * CHOL_NB));
     GP_TRY(alloc(Linv, (size_t)ldn * n)); GP_TRY(alloc(Tmp, (size_t)ldn * n)); GP_TRY(alloc(kstar2, (size_t)ldn * kcols));
-    GP_TRY(alloc(panel_scratch, (size_t)ldn * CHOL_NB));
-    lookahead.panel_scratch = panel_scratch; lookahead.ld_scratch = ldn;
+    GP_TRY(alloc(chol_flags, (size_t)ceil_div(n, CHOL_NB) + 1));
     GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
     GP_TRY(alloc(kstar, (size_t)ldn * kcols)); GP_TRY(alloc(s, std::max((size_t)ldN, kcols)));
@@ -337,7 +337,7 @@ int gpirt_b200_sampler::step_rebuild() {
     GP_TRY(launch_se_cov(stream, theta, n, theta, n, 0.001, true, L, ldn));
     toc();
     tic(GPIRT_B200_T_CHOL);
-    GP_TRY(potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, &lookahead));
+    GP_TRY(potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, chol_flags, &lookahead));
     toc();
     if (solve_mode == 0) {
         tic(GPIRT_B200_T_TRTRI);   // L^-1 once per sweep: every triangular solve of draw_fstar becomes a triangular GEMM
@@ -658,7 +658,7 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         return GPIRT_B200_OK;
     };
     tic(GPIRT_B200_T_CHOL);
-    int rc = potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, &lookahead);
+    int rc = potrf_lower_rl(stream, L, ldn, n, Dinv, ldn, status, chol_flags, &lookahead);
     lookahead.after_panel = nullptr;
     GP_TRY(rc);
     toc();
@@ -716,7 +716,7 @@ void gpirt_b200_sampler::destroy() {
     ti8.destroy();
     dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
     void* ptrs[] = {work, y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
-                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, panel_scratch};
+                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, chol_flags};
     for (void* p : ptrs) pool_free(p, stream);
     if (stream) cudaStreamSynchronize(stream);
     if (stream) cudaStreamDestroy(stream);
