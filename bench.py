@@ -85,64 +85,72 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's loop body on host cores, on a bounded item sample
+# CPU arm: the reference's loop body (its own sources, oracle/_ref; else the oracle port) on host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sweeps(cfg, data, steps, warmup, budget_s, threads):
-    """Times `steps` sweeps of the reference CPU path on the first m_s items (all n respondents) and extrapolates
-    T(m) = T_fixed + (T(m_s) - T_fixed) * m / m_s  (every step but K/Cholesky and the L^-1 K* solve is linear in m)."""
+def cpu_reference_sweeps(n, m, data, steps, warmup, m_s, threads, n_sub=None, seed=12345):
+    """Times `steps` sweeps of the reference CPU path on the first m_s items and, for the theta step only, on n_sub evenly
+    spaced respondents (all n respondents everywhere else: K, chol, the ESS, the solves and the beta step need the full
+    n x n factor).  m_s == m and n_sub == n is a MEASURED full sweep.  Otherwise the full-size sweep is EXTRAPOLATED:
+        T(m) = T_fixed + T_item m / m_s,   T_item = draw_f + per-item part of draw_fstar + draw_theta n / n_sub + draw_beta
+    Every step but K / Cholesky and the K* solve (T_fixed, measured at full size) is exactly linear in m, and draw_theta is
+    exactly linear in the number of respondents (src/draw-theta.cpp:12-34 loops over them independently)."""
     from oracle import oracle as O
-    n, m = cfg["n"], cfg["m"]
+    n_sub = n if n_sub is None else min(n, n_sub)
+    m_s = min(m, m_s)
     use_ref = os.path.exists(O.REF_SO)
     O.set_blas_threads(threads)
-    per_item = 1.35e-7 * n * N_GRID + 1.2e-8 * n * n       # rough seconds/item (theta grid loop + three O(n^2) passes)
-    fixed = 6e-11 * n ** 3 / max(1, min(threads, 8)) + 2e-8 * n * n
-    m_s = int(max(4, min(m, 128, (budget_s / max(1, steps + warmup) - fixed) / per_item)))
     y = np.asfortranarray(data["y"][:, :m_s])
+    I = np.unique(np.linspace(0, n - 1, n_sub).astype(int))
+    y_sub = np.asfortranarray(y[I, :])
     pm, psd, pstep = data["pm"][:, :m_s], data["psd"][:, :m_s], data["pstep"][:, :m_s]
     theta = data["theta_init"].copy()
     ts, prior = O.grid()
     if use_ref:
-        O.ref().gpref_seed(12345)
+        O.ref().gpref_seed(seed)
         def chol(th):
             S = O.ref_K(th, th)                                # K(theta, theta), gpirtMCMC.cpp:76
             S[np.diag_indices(n)] += 0.001                     # :77
             return O.ref_chol_lower(S)                         # :78
         draw_f = lambda f, L, mu: O.ref_draw_f(f, y, L, mu)                      # noqa: E731
         draw_fstar = lambda f, th, L, mus: O.ref_draw_fstar(f, th, ts, L, mus)   # noqa: E731
-        draw_theta = lambda fs, mus: O.ref_draw_theta(ts, y, prior, fs, mus)     # noqa: E731
+        draw_theta = lambda fs, mus: O.ref_draw_theta(ts, y_sub, prior, fs, mus)     # noqa: E731
         draw_beta = lambda b, th, f: O.ref_draw_beta(b, th, y, f, pm, psd, pstep)  # noqa: E731
         kind = "reference"
     else:
-        rng = O.Rng.keyed(12345)
+        rng = O.Rng.keyed(seed)
         chol = lambda th: O.build_cholS(th)                                      # noqa: E731
         draw_f = lambda f, L, mu: O.draw_f(f, y, L, mu, rng)[0]                  # noqa: E731
         draw_fstar = lambda f, th, L, mus: O.draw_fstar(f, th, ts, L, mus, rng)[0]  # noqa: E731
-        draw_theta = lambda fs, mus: O.draw_theta(ts, y, prior, fs, rng, mode=0)[0]  # noqa: E731
+        draw_theta = lambda fs, mus: O.draw_theta(ts, y_sub, prior, fs, rng, mode=0)[0]  # noqa: E731
         draw_beta = lambda b, th, f: O.draw_beta(b, th, y, f, pm, psd, pstep, rng)[0]  # noqa: E731
         kind = "port"
     rs = np.random.RandomState(7)
     L = chol(theta)
     f = np.asfortranarray(L @ rs.randn(n, m_s))
     beta = np.asfortranarray(rs.randn(2, m_s) * 3.0)
-    t_sweep, t_fixed = [], []
+    parts = {k: [] for k in ("draw_f", "draw_fstar", "draw_theta", "draw_beta", "rebuild", "step")}
     for it in range(warmup + steps):
         if kind == "port":
             rng.set_sweep(it + 1)
         mu, mus = O.linear_mean(theta, beta), O.linear_mean(ts, beta)
         t0 = time.perf_counter()
         f = draw_f(f, L, mu)                                   # gpirtMCMC.cpp:68
+        t1 = time.perf_counter()
         fs = draw_fstar(f, theta, L, mus)                      # :69
+        t2 = time.perf_counter()
         th_new = draw_theta(fs, mus)                           # :70
-        if not np.all(np.isfinite(th_new)):                    # the reference's theta_star[N] read (SURVEY F3) — cannot
-            th_new = np.where(np.isfinite(th_new), th_new, theta)  # happen at m_s <= 128; guard keeps the run alive
-        theta = th_new
+        t3 = time.perf_counter()
+        ok = np.isfinite(th_new)                               # the reference's theta_star[N] read (SURVEY F3) cannot happen
+        theta[I[ok]] = th_new[ok]                              # at m_s <= 128; the guard keeps a full-size run alive
         beta = draw_beta(beta, theta, f)                       # :72
         mu, mus = O.linear_mean(theta, beta), O.linear_mean(ts, beta)   # :74-75
-        t1 = time.perf_counter()
+        t4 = time.perf_counter()
         L = chol(theta)                                        # :76-78
-        t2 = time.perf_counter()
+        t5 = time.perf_counter()
         if it >= warmup:
-            t_sweep.append(t2 - t0); t_fixed.append(t2 - t1)
+            for k, v in zip(("draw_f", "draw_fstar", "draw_theta", "draw_beta", "rebuild", "step"),
+                            (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0)):
+                parts[k].append(v)
     # fixed part of draw_fstar (K*, L^-1 K*): time it with a single item
     t0 = time.perf_counter()
     if use_ref:
@@ -150,15 +158,107 @@ def cpu_reference_sweeps(cfg, data, steps, warmup, budget_s, threads):
     else:
         O.draw_fstar(f[:, :1], theta, ts, L, O.linear_mean(ts, beta[:, :1]), rng)
     t_fs1 = time.perf_counter() - t0
-    T_s, T_fix = float(np.mean(t_sweep)), float(np.mean(t_fixed)) + t_fs1
-    T_full = T_fix + max(0.0, T_s - T_fix) * (m / m_s)
-    sample = ("%d sweep(s) of the %s on the first %d of %d items (all %d respondents), %.2f s/sweep measured; "
-              "extrapolated linearly in m to %.1f s/sweep (fixed part K+chol+L^-1K* %.2f s)" %
-              (steps, "reference sources (oracle/_ref)" if use_ref else "oracle port", m_s, m, n, T_s, T_full, T_fix))
-    if m_s == m:
-        sample = "%d full sweep(s) of the %s, %.2f s/sweep" % (steps, "reference sources (oracle/_ref)" if use_ref else "oracle port", T_s)
+    mean = {k: float(np.mean(v)) for k, v in parts.items()}
+    T_fix = mean["rebuild"] + t_fs1
+    T_item = mean["draw_f"] + max(0.0, mean["draw_fstar"] - t_fs1) + mean["draw_theta"] * (n / len(I)) + mean["draw_beta"]
+    full = m_s == m and len(I) == n
+    T_full = mean["step"] if full else T_fix + T_item * (m / m_s)
+    src = "reference sources (oracle/_ref)" if use_ref else "oracle port"
+    if full:
+        sample = "%d MEASURED full sweep(s) of the %s at %d x %d, %.2f s/sweep" % (steps, src, n, m, T_full)
+    else:
+        sample = ("%d sweep(s) of the %s on the first %d of %d items (theta step on %d of %d respondents), %.2f s per sampled "
+                  "sweep measured; EXTRAPOLATED linearly in m (and in n for the theta step) to %.1f s/sweep (fixed part "
+                  "K+chol+L^-1K* %.2f s)" % (steps, src, m_s, m, len(I), n, mean["step"], T_full, T_fix))
     return dict(value=1.0 / T_full, unit="sweeps/s", cores=threads if threads > 1 else 1, kind=kind, sample=sample,
-                blas_threads=threads, sampler_threads=1, s_per_sweep=T_full, measured_s=float(np.sum(t_sweep)))
+                blas_threads=threads, sampler_threads=1, s_per_sweep=T_full, extrapolated=not full,
+                sample_s_per_step=mean["step"], measured_s=float(np.sum(parts["step"])), items=m_s, respondents_theta=len(I),
+                per_step_s={k: mean[k] for k in ("draw_f", "draw_fstar", "draw_theta", "draw_beta", "rebuild")},
+                fixed_s=T_fix)
+
+
+def cpu_fixed_part_by_blas_threads(n, theta, thread_counts):
+    """K + Cholesky and the K* solve of one sweep (the BLAS/LAPACK-bound part, gpirtMCMC.cpp:76-78, draw-fstar.cpp:17-19) at
+    each BLAS thread count; the sampler code around it is single-threaded like the reference."""
+    from oracle import oracle as O
+    ts, _ = O.grid()
+    out = {}
+    use_ref = os.path.exists(O.REF_SO)
+    for t in thread_counts:
+        O.set_blas_threads(t)
+        t0 = time.perf_counter()
+        if use_ref:
+            S = O.ref_K(theta, theta); S[np.diag_indices(n)] += 0.001
+            L = O.ref_chol_lower(S)
+        else:
+            L = O.build_cholS(theta)
+        t1 = time.perf_counter()
+        f1 = np.zeros((n, 1), order="F")
+        if use_ref:
+            O.ref_draw_fstar(f1, theta, ts, L, np.zeros((1001, 1), order="F"))
+        else:
+            O.draw_fstar(f1, theta, ts, L, np.zeros((1001, 1), order="F"), O.Rng.keyed(1))
+        t2 = time.perf_counter()
+        out[str(t)] = {"k_chol_s": t1 - t0, "kstar_solve_s": t2 - t1}
+    return out
+
+
+def cpu_reference_chain_ess(y, theta_init, S, B):
+    """theta ESS/s of the reference's own gpirtMCMC() (oracle/_ref) on a small problem: the second half of BASELINE's metric"""
+    from oracle import oracle as O
+    from gpirt_b200.diagnostics import ess_geyer
+    if not os.path.exists(O.REF_SO):
+        return None
+    m = y.shape[1]
+    O.ref().gpref_seed(2026)
+    t0 = time.perf_counter()
+    r = O.ref_mcmc(np.asarray(y), theta_init, S, B, np.zeros((2, m)), np.full((2, m), 3.0), np.full((2, m), 0.1))
+    el = time.perf_counter() - t0
+    ess = ess_geyer(r["theta"][1:])
+    ess = ess[np.isfinite(ess)]
+    return {"samples": S, "burn": B, "seconds": el, "s_per_sweep_measured": el / (S + B), "sweeps_per_s": (S + B) / el,
+            "ess_median": float(np.median(ess)), "ess_per_sec_median": float(np.median(ess) / el),
+            "ess_per_sec_min": float(ess.min() / el), "note": "MEASURED full chain of the reference's own gpirtMCMC()"}
+
+
+def shard_check(G, dist, rank, world, local_rank, fresh_uid):
+    """N > 1: before anything is timed, the item-sharded sampler (CUDA path, NCCL exchanges) must reproduce the single-GPU
+    chain on a small problem that takes the same code paths (fixed-point products, pipelined sweep, blocked-substitution
+    solves).  Every rank compares its own item block with an unsharded run on its own GPU; the worst difference over ranks
+    is returned.  Same solve route: bit-identical (addressed RNG, integer accumulation); default single-GPU route (through
+    L^-1): theta identical, values to rounding."""
+    import torch
+    from gpirt_b200 import ResponseMatrix
+    from gpirt_b200.sharding import item_block
+    n, m, S, B = 640, 600, 2, 1
+    d = synthetic.make(n, m, seed=77, missing=0.05)
+    j0, j1 = item_block(m, rank, world)
+    kw = dict(theta_init=d["theta_init"], seed=99, device=local_rank)
+    got = G.gpirtMCMC(ResponseMatrix(d["y"][:, j0:j1]), S, B, beta_prior_means=d["pm"][:, j0:j1], beta_prior_sds=d["psd"][:, j0:j1],
+                      beta_proposal_sds=d["pstep"][:, j0:j1], shard=(rank, world, m, j0, fresh_uid()), **kw)
+    diffs = {}
+    for route in ("1", None):
+        old = os.environ.get("GPIRT_SOLVE_MODE")
+        if route is not None:
+            os.environ["GPIRT_SOLVE_MODE"] = route
+        try:
+            full = G.gpirtMCMC(ResponseMatrix(d["y"]), S, B, beta_prior_means=d["pm"], beta_prior_sds=d["psd"],
+                               beta_proposal_sds=d["pstep"], **kw)
+        finally:
+            if route is not None:
+                if old is None:
+                    os.environ.pop("GPIRT_SOLVE_MODE", None)
+                else:
+                    os.environ["GPIRT_SOLVE_MODE"] = old
+        v = [float(not np.array_equal(got["theta"], full["theta"])), float(np.max(np.abs(got["beta"] - full["beta"][:, j0:j1]))),
+             float(np.max(np.abs(got["f"] - full["f"][:, j0:j1]))), float(np.max(np.abs(got["IRFs"] - full["IRFs"][:, j0:j1])))]
+        t = torch.tensor(v, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        diffs["same_route" if route else "default_route"] = dict(zip(("theta_differs", "max_dbeta", "max_df", "max_dirf"), t.tolist()))
+    a, b = diffs["same_route"], diffs["default_route"]
+    ok = (a["theta_differs"] == 0 and a["max_dbeta"] == 0 and a["max_df"] == 0 and a["max_dirf"] == 0 and
+          b["theta_differs"] == 0 and b["max_dbeta"] <= 1e-9 and b["max_df"] <= 1e-7 and b["max_dirf"] <= 1e-7)
+    return {"status": "ok" if ok else "FAILED", "shape": "%d x %d, %d sweeps, 5%% missing, world %d" % (n, m, S + B, world), **diffs}
 
 
 def main():
@@ -190,11 +290,24 @@ def main():
         if rank != 0:
             return 0
         data = synthetic.make(n, m)
-        res = cpu_reference_sweeps(cfg, data, K, W, budget_s=150.0, threads=host_threads)
+        # every step is one sampled sweep: all respondents, an item sample sized so that K + W steps end within a few
+        # minutes (the same 64-item sample as the cpu_baseline leg of the B200 arm whenever that fits), the theta step on a
+        # respondent sample.  Small workloads (c1, c2 with few steps) run whole.
+        per_item = 2.2e-8 * n * N_GRID * min(1.0, 256.0 / n) + 1.4e-8 * n * n    # rough seconds per item of a sampled sweep
+        fixed = 8e-11 * n ** 3 / max(1, min(host_threads, 8)) + 2e-8 * n * n
+        budget = 240.0 / max(1, K + W)
+        m_s = int(max(8, min(m, 64, (budget - fixed) / per_item)))
+        whole = n * float(N_GRID) * m * 2.2e-8 * (K + W) < 240.0
+        res = cpu_reference_sweeps(n, m, data, K, W, m if whole else m_s, host_threads, n_sub=None if whole else 256)
         line = {"impl": "reference", "metric": "gibbs_sweeps_per_sec", "value": res["value"], "unit": "sweeps/s", "n_gpus": args.gpus,
-                "steps": K, "warmup": W, "ms_per_step": 1000.0 * res["s_per_sweep"], "higher_is_better": True,
+                "steps": K, "warmup": W, "ms_per_step": 1000.0 * res["sample_s_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "note": "ms_per_step is the MEASURED time of one sampled step (see cpu_baseline.sample); value is the full-size "
+                        "throughput, 1 / ms_per_full_sweep%s" % ("" if not res["extrapolated"] else
+                                                                 ", EXTRAPOLATED from the sample (exactly linear parts only)"),
+                "ms_per_full_sweep": 1000.0 * res["s_per_sweep"], "extrapolated": res["extrapolated"],
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "blas_threads", "sampler_threads",
+                                                       "items", "respondents_theta", "per_step_s", "fixed_s")},
                 "e2e": {"value": res["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -214,6 +327,13 @@ def main():
         def fresh_uid():   # one ncclUniqueId per communicator
             return share_unique_id(dist, rank, G.nccl_unique_id, device="cuda")
         uid = fresh_uid()
+    shard_ok = shard_check(G, dist, rank, world, local_rank, fresh_uid) if world > 1 else None
+    if shard_ok is not None and shard_ok["status"] != "ok":
+        if rank == 0:
+            print(json.dumps({"metric": "gibbs_sweeps_per_sec", "value": None, "n_gpus": world, "shard_check": shard_ok,
+                              "error": "the sharded sampler does not reproduce the single-GPU chain; nothing was timed"}))
+        dist.destroy_process_group()
+        return 1
     data = synthetic.make(n, m)
     # contiguous item block of this rank
     from gpirt_b200.sharding import item_block
@@ -285,18 +405,21 @@ def main():
     iso_ms = sum(t_iso[k][0] for k in segs) / Ki
     i8_note = None
     if dom == "k_dgemm_i8":
-        # tcgen05 kind::i8 issues twice the multiply-adds per instruction of kind::f16 (K = 32 vs 16), so the int8
-        # ceiling is 2 x the measured dense bf16 figure: sustained inside the long step, burst for the kernel alone
+        # the int8 ceiling is MEASURED in this run: tcgen05.mma.kind::i8 (M128 N256 K32, operands in shared memory) issued
+        # back to back on every SM (gpirt_b200_int8_peak_tops); MEASURED_PEAKS.json has no int8 figure
+        i8_peak = G.int8_peak_tops()
         alg = 36.0 * fp64_work
-        peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        iso_peak = 2.0 * peaks["bf16_tflops"]
-        achieved, iso, unit = alg / dom_ms * 1e-9, alg / iso_ms * 1e-9, "TFLOP/s"
-        peak_src = "2 x dense bf16 (%s) = int8 tensor ops/s; nominal int8 dense is 4500" % peak_src
+        peak = iso_peak = i8_peak
+        achieved, iso, unit = alg / dom_ms * 1e-9, alg / iso_ms * 1e-9, "TOP/s"
+        peak_src = ("tcgen05.mma.kind::i8 issue-rate microbenchmark measured in this run (%.0f TOP/s; nominal dense int8 4500; "
+                    "2 x the dense bf16 figure of MEASURED_PEAKS.json would be %.0f)" % (i8_peak, 2.0 * peaks["bf16_tflops"]))
         i8_note = {"plane_pair_products": 36, "fp64_tensor_peak_tflops": dmma,
                    "fp64_equivalent_tflops": fp64_work / dom_ms * 1e-9, "fp64_equivalent_tflops_isolated": fp64_work / iso_ms * 1e-9,
-                   "frac_of_nominal_int8_isolated": iso / 4500.0,
                    "segments_ms": {k: seg_ms[k] for k in segs}, "segments_ms_isolated": {k: t_iso[k][0] / Ki for k in segs},
-                   "note": "segment times include the operand slicing kernels of each product"}
+                   "note": "`achieved` counts the 36 exact int8 plane-pair products the scheme EXECUTES per FP64 product; the "
+                           "algorithmic work of SURVEY 8(d) is the FP64 product itself: see fp64_equivalent_frac (FP64 flop / "
+                           "measured FP64 tensor peak; > 1 means faster than any FP64-pipe GEMM could be).  Segment times include "
+                           "the operand slicing kernels of each product"}
         bound = "tensor"
     elif bound == "tensor":
         alg = fp64_work
@@ -321,6 +444,12 @@ def main():
                 "isolated": {"achieved": iso, "peak": iso_peak, "frac": iso / iso_peak, "ms_per_sweep": iso_ms,
                              "sweep_ms_unpipelined": ms_iso / Ki},
                 "fixed_point": i8_note,
+                "fp64_equivalent_frac": (fp64_work / dom_ms * 1e-9) / dmma if bound == "tensor" else None,
+                "fp64_equivalent_frac_isolated": (fp64_work / iso_ms * 1e-9) / dmma if bound == "tensor" else None,
+                "cholesky": {"ms_isolated": t_iso["chol"][0] / Ki, "ms_pipelined": timers["chol"][0] / K,
+                             "tflops_isolated": n ** 3 / 3.0 / (t_iso["chol"][0] / Ki) * 1e-9,
+                             "frac_of_fp64_tensor_peak_isolated": n ** 3 / 3.0 / (t_iso["chol"][0] / Ki) * 1e-9 / dmma,
+                             "note": "potrf_lower_rl: k_diag128 + k_panel_update chain with look-ahead bulk updates on gemm_f64_kernel"},
                 "per_step_ms": {k: v[0] / K for k, v in timers.items() if v[1]},
                 "per_step_ms_isolated": {k: v[0] / Ki for k, v in t_iso.items() if v[1]}}
     s.close()
@@ -328,6 +457,8 @@ def main():
     line = {"metric": "gibbs_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": max(3, W),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+    if shard_ok is not None:
+        line["shard_check"] = shard_ok
 
     # ------------------------------------------------------------------ chain-parallel mode (BASELINE config 4), N > 1 only
     # every rank runs an INDEPENDENT chain of the whole workload (own seed, no communication): aggregate sweeps/s
@@ -375,6 +506,19 @@ def main():
                        "note": "gpirtMCMC(sample_iterations=%d, burn_iterations=0) wall time incl. setup, initial draws, H2D of y "
                                "and D2H of every theta/beta/f draw (reference output contract)" % Ke}
         del out
+        if world == 1 and not args.no_extras:
+            # the same public call keeping every 10th sampling iteration (opts.thin) and the posterior mean / sd of f
+            # accumulated on the device: the n x m x (S+1) array of f draws is what bounds `e2e`
+            St = 100
+            t0 = time.perf_counter()
+            out = G.gpirtMCMC(yrm, St, 0, thin=10, f_summary=True, **common)
+            el_t = time.perf_counter() - t0
+            assert out["f"].shape[2] == St // 10 + 1 and np.isfinite(out["f_mean"]).all()
+            line["e2e"]["thin10"] = {"value": St / el_t, "unit": "sweeps/s", "frac_of_value": (St / el_t) / value,
+                                     "d2h_bytes_per_step": int((n * m_loc + 2 * m_loc + n) * 8 * (St // 10 + 1) / St + (N_GRID + 2 * n) * m_loc * 8 / St),
+                                     "note": "gpirtMCMC(%d, 0, thin=10, f_summary=True): every 10th draw of theta / beta / f stored, "
+                                             "f mean and sd over all %d iterations returned" % (St, St)}
+            del out
 
     # ------------------------------------------------------------------ theta ESS/sec (second half of BASELINE's metric), N = 1 only
     if rank == 0 and world == 1 and not args.no_extras:
@@ -405,27 +549,65 @@ def main():
     # ------------------------------------------------------------------ the other single-GPU configs, briefly (N = 1 only)
     if rank == 0 and world == 1 and args.workload == "c3" and not args.no_extras:
         extras = {}
-        for wl in ("c1", "c2"):
+        for wl, miss, k2 in (("c1", 0.0, 200), ("c2", 0.0, 50), ("c3", 0.05, 10), ("c5", 0.0, 5)):
+            key = wl if miss == 0.0 else "%s_missing%d" % (wl, int(100 * miss))
             try:
                 c = synthetic.WORKLOADS[wl]
-                d2 = synthetic.make(c["n"], c["m"])
+                d2 = synthetic.make(c["n"], c["m"], missing=miss)
                 s2 = G.Sampler(d2["y"], d2["theta_init"], d2["pm"], d2["psd"], d2["pstep"], seed=synthetic.SEED, device=local_rank)
-                s2.set_timing(False)
                 s2.init_draws()
-                s2.sweep(5)
-                k2 = 50
+                s2.sweep(3)
+                s2.set_timing(False)                 # the per-step events cost as much as the kernels at the small shapes
                 ms2 = s2.sweep(k2)
-                extras[wl] = {"n": c["n"], "m": c["m"], "value": 1000.0 * k2 / ms2, "unit": "sweeps/s", "ms_per_step": ms2 / k2, "steps": k2}
+                s2.set_timing(True)
+                s2.timings(reset=True)
+                s2.sweep(min(k2, 20))
+                t2 = {k: (v[0] * k2 / min(k2, 20), v[1]) for k, v in s2.timings().items()}
+                extras[key] = {"n": c["n"], "m": c["m"], "missing": miss, "value": 1000.0 * k2 / ms2, "unit": "sweeps/s",
+                               "ms_per_step": ms2 / k2, "steps": k2, "per_step_ms": {k: v[0] / k2 for k, v in t2.items() if v[1]}}
+                if wl == "c5":   # the large-n configuration: Cholesky roofline and footprint
+                    s2.set_pipeline(False)
+                    s2.sweep(1); s2.timings(reset=True); s2.sweep(2)
+                    ti = s2.timings()
+                    nn = c["n"]
+                    extras[key]["cholesky"] = {"ms_isolated": ti["chol"][0] / 2, "tflops_isolated": nn ** 3 / 3.0 / (ti["chol"][0] / 2) * 1e-9,
+                                               "frac_of_fp64_tensor_peak_isolated": nn ** 3 / 3.0 / (ti["chol"][0] / 2) * 1e-9 / dmma}
+                    extras[key]["hbm_footprint_gb"] = (6 * nn * nn * 8 + 3 * nn * c["m"] * 8 + 11 * nn * c["m"] + 3 * 1008 * c["m"] * 8 + 16 * nn * nn) / 1e9
                 s2.close()
+                del d2, s2
             except Exception as ex:
-                extras[wl] = {"error": repr(ex)}
+                extras[key] = {"error": repr(ex)}
         line["other_workloads"] = extras
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            res = cpu_reference_sweeps(cfg, data, 1, 0, budget_s=20.0, threads=host_threads)
-            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # the bench workload: one sampled sweep (64 items, theta step on 256 respondents), extrapolated as stated in `sample`
+            res = cpu_reference_sweeps(n, m, data, 1, 0, 64, host_threads, n_sub=256)
+            cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "blas_threads", "sampler_threads", "items",
+                                      "respondents_theta", "per_step_s", "fixed_s", "extrapolated")}
+            if not args.no_extras:
+                cb["fixed_part_by_blas_threads"] = cpu_fixed_part_by_blas_threads(n, data["theta_init"], sorted({1, min(8, host_threads), host_threads}))
+                # MEASURED full sweeps of the reference at the small configurations, and its theta ESS/s on the real data set
+                c2 = synthetic.WORKLOADS["c2"]
+                r2 = cpu_reference_sweeps(c2["n"], c2["m"], synthetic.make(c2["n"], c2["m"]), 1, 0, c2["m"], host_threads)
+                cb["c2_full_sweep"] = {k: r2[k] for k in ("value", "unit", "sample", "per_step_s", "extrapolated")}
+                import warnings
+                import gpirt_b200
+                codes, _, _ = gpirt_b200.senate116()
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    y1 = gpirt_b200.response_matrix(codes)
+                th1 = np.random.RandomState(116).randn(y1.shape[0])
+                cb["c1_senate116_chain"] = cpu_reference_chain_ess(y1, th1, 30, 10)
+                t0 = time.perf_counter()
+                g1 = G.gpirtMCMC(y1, 300, 100, theta_init=th1, seed=116, device=local_rank, store_f=False)
+                el1 = time.perf_counter() - t0
+                from gpirt_b200.diagnostics import ess_geyer
+                e1 = ess_geyer(g1["theta"][1:]); e1 = e1[np.isfinite(e1)]
+                cb["c1_senate116_chain_b200"] = {"samples": 300, "burn": 100, "seconds": el1, "sweeps_per_s": 400 / el1,
+                                                 "ess_median": float(np.median(e1)), "ess_per_sec_median": float(np.median(e1) / el1)}
+            line["cpu_baseline"] = cb
         except Exception as ex:  # the baseline is informative; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "sweeps/s", "cores": host_threads, "kind": "port", "sample": "failed: %r" % (ex,)}
     if dist is not None:

@@ -8,6 +8,7 @@
 #include "dgemm_i8.cuh"
 #include "kernels.cuh"
 #include "linalg.cuh"
+#include "theta_int8.cuh"
 
 using namespace gpirt;
 
@@ -227,6 +228,11 @@ int gpirt_b200_fp64_peak_tflops(double* dmma_tflops, double* dfma_tflops) {
     return GPIRT_B200_OK;
 }
 
+int gpirt_b200_int8_peak_tops(double* tops) {
+    GP_TRY(have_device());
+    return int8_peak_tops(tops);
+}
+
 int gpirt_b200_rng_probe(uint64_t seed, uint32_t sweep, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
                          double* uniforms, double* normals) {
     if (count < 0 || !uniforms || !normals) return GPIRT_B200_ERR_ARG;
@@ -234,7 +240,7 @@ int gpirt_b200_rng_probe(uint64_t seed, uint32_t sweep, uint32_t purpose, uint32
     if (count == 0) return GPIRT_B200_OK;
     DevBuf u, z;
     GP_TRY(u.alloc(count)); GP_TRY(z.alloc(count));
-    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), sweep};
+    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), sweep, nullptr};
     GP_TRY(launch_rng_probe(0, key, purpose, stream, idx0, count, u.p, z.p));
     GP_CUDA(cudaMemcpy(uniforms, u.p, count * sizeof(double), cudaMemcpyDeviceToHost));
     GP_CUDA(cudaMemcpy(normals, z.p, count * sizeof(double), cudaMemcpyDeviceToHost));

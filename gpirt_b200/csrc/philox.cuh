@@ -11,7 +11,10 @@ enum Purpose : uint32_t {
     P_INIT_F_Z = 0, P_INIT_BETA = 1, P_ESS_Z = 2, P_ESS_U = 3, P_FSTAR_Z = 4, P_THETA_U = 5, P_BETA_Z = 6, P_BETA_U = 7
 };
 
-struct RngKey { uint32_t k0, k1, sweep; };
+// sweep_dev (optional): device word added to `sweep` at run time — lets a CUDA graph of a whole sweep be replayed with a
+// new sweep counter (a one-thread kernel inside the graph bumps the word) without touching kernel parameters.
+struct RngKey { uint32_t k0, k1, sweep; const uint32_t* sweep_dev; };
+__device__ __forceinline__ uint32_t rng_sweep(const RngKey& key) { return key.sweep_dev ? key.sweep + *key.sweep_dev : key.sweep; }
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
                                                        uint32_t k0, uint32_t k1) {
@@ -36,7 +39,7 @@ __host__ __device__ __forceinline__ double u01_from_bits(uint32_t lo, uint32_t h
 }
 
 __device__ __forceinline__ double rng_uniform(const RngKey& key, uint32_t purpose, uint32_t stream, uint32_t idx) {
-    uint32_t c0 = idx, c1 = stream, c2 = purpose, c3 = key.sweep;
+    uint32_t c0 = idx, c1 = stream, c2 = purpose, c3 = rng_sweep(key);
     philox4x32_10(c0, c1, c2, c3, key.k0, key.k1);
     return u01_from_bits(c0, c1);
 }
@@ -44,7 +47,7 @@ __device__ __forceinline__ double rng_uniform(const RngKey& key, uint32_t purpos
 // both members of the Box-Muller pair with counter `pair` (elements 2*pair and 2*pair+1 of the stream)
 __device__ __forceinline__ void rng_normal_pair(const RngKey& key, uint32_t purpose, uint32_t stream, uint32_t pair,
                                                 double& z_even, double& z_odd) {
-    uint32_t c0 = pair, c1 = stream, c2 = purpose, c3 = key.sweep;
+    uint32_t c0 = pair, c1 = stream, c2 = purpose, c3 = rng_sweep(key);
     philox4x32_10(c0, c1, c2, c3, key.k0, key.k1);
     double u1 = u01_from_bits(c0, c1), u2 = u01_from_bits(c2, c3);
     double r = sqrt(-2.0 * log(u1));

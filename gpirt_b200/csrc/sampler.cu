@@ -126,7 +126,7 @@ struct gpirt_b200_sampler {
 
     Seg tic_on(int timer, cudaStream_t st) {
         Seg sg{timer, nullptr, nullptr};
-        if (!timing) return sg;
+        if (!timing || capturing) return sg;
         sg.a = get_event(); sg.b = get_event();
         cudaEventRecord(sg.a, st);
         return sg;
@@ -142,12 +142,12 @@ struct gpirt_b200_sampler {
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
     void tic(int timer) {
-        if (!timing) return;
+        if (!timing || capturing) return;
         cur.timer = timer; cur.a = get_event(); cur.b = get_event();
         cudaEventRecord(cur.a, stream);
     }
     void toc() {
-        if (!timing) return;
+        if (!timing || capturing) return;
         cudaEventRecord(cur.b, stream);
         pending.push_back(cur);
     }
@@ -161,7 +161,23 @@ struct gpirt_b200_sampler {
         cudaGetLastError();   // a not-ready event must not surface later as a launch failure
     }
 
-    RngKey key_at(uint32_t sweep) const { RngKey k = key; k.sweep = sweep; return k; }
+    // while a sweep is being captured into a graph the kernels get the sweep counter relative to the captured sweep plus
+    // the device word the graph bumps on every replay
+    RngKey key_at(uint32_t sweep) const {
+        RngKey k = key;
+        k.sweep = capturing ? sweep - capture_base : sweep;
+        k.sweep_dev = capturing ? d_sweep : nullptr;
+        return k;
+    }
+    // ---- CUDA graph of the un-pipelined sweep (small n: the sweep is ~40 short kernels and pure launch latency) ----
+    bool graph_enabled = true, capturing = false, warmed = false;
+    uint32_t capture_base = 0;
+    uint32_t* d_sweep = nullptr;          // device copy of the sweep counter read by the captured kernels
+    uint32_t d_sweep_value = 0xffffffffu; // what *d_sweep holds (host mirror)
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // [accumulate_irf]
+    int64_t graph_kernels = 0;            // kernels per sweep (counted on the eager path; a graph replay launches the same ones)
+    int sweep_eager(uint32_t t, int accumulate);
+    int sweep_graph(uint32_t t, int accumulate);
 
     template <typename T> int alloc(T*& p, size_t count) {
         void* q = nullptr;
@@ -222,7 +238,11 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         return GPIRT_B200_ERR_CUDA;
     }
     if (o && opts.device >= 0) GP_CUDA(cudaSetDevice(opts.device));
-    key.k0 = (uint32_t)opts.seed; key.k1 = (uint32_t)(opts.seed >> 32); key.sweep = 0;
+    key.k0 = (uint32_t)opts.seed; key.k1 = (uint32_t)(opts.seed >> 32); key.sweep = 0; key.sweep_dev = nullptr;
+    {
+        const char* ge = getenv("GPIRT_GRAPH");
+        graph_enabled = ge ? atoi(ge) != 0 : opts.use_graph >= 0;
+    }
     if (opts.world_size > 1) {
         item_offset = (uint32_t)opts.item_offset;
         GP_TRY(comm_init(comm, opts.rank, opts.world_size, opts.nccl_unique_id));
@@ -238,7 +258,9 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_CUDA(cudaStreamCreateWithPriority(&st_trsm, cudaStreamNonBlocking, greatest));
         for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         const char* sm = getenv("GPIRT_SOLVE_MODE");
-        solve_mode = sm ? atoi(sm) : (comm.world > 1 ? 1 : 0);
+        // through L^-1 (n^3/3 for the inverse + two triangular products) or by blocked substitution behind the Cholesky panels
+        // (2 n^2 x 1001): substitution wins when few right-hand sides are left per rank, and on one GPU once n/3 > 2 x 1001
+        solve_mode = sm ? atoi(sm) : ((comm.world > 1 || n > 6144) ? 1 : 0);
         if (opts.fstar_mode != 0) solve_mode = 0;   // the literal per-item form needs L^-1
         const char* pe = getenv("GPIRT_PIPELINE");
         if (pe) pipeline = atoi(pe) != 0;
@@ -265,6 +287,7 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(kstar, (size_t)ldn * kcols)); GP_TRY(alloc(s, std::max((size_t)ldN, kcols)));
     GP_TRY(alloc(logPt, (size_t)ldN * (n + 1))); GP_TRY(alloc(partial, (size_t)N_CHUNKS * N_GRID));
     GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2)); GP_TRY(alloc(work, 4));
+    GP_TRY(alloc(d_sweep, 2));
     GP_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int), stream));
     GP_CUDA(cudaMemsetAsync(Dinv, 0, (size_t)ldn * CHOL_NB * sizeof(double), stream));   // the factorisation writes the lower triangles only
     GP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream));
@@ -687,8 +710,9 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
     return GPIRT_B200_OK;
 }
 
-int gpirt_b200_sampler::sweep(int accumulate) {
-    const uint32_t t = ++sweep_counter;
+__global__ void k_bump_sweep(uint32_t* sweep) { *sweep += 1u; }
+
+int gpirt_b200_sampler::sweep_eager(uint32_t t, int accumulate) {
     const bool can_pipe = pipeline && ceil_div(n, CHOL_NB) > 2;   // the look-ahead factorisation needs > 2 panels
     if (can_pipe && nu_ready && nu_sweep == t) GP_TRY(ess_only(t));
     else GP_TRY(step_draw_f(t));
@@ -701,8 +725,61 @@ int gpirt_b200_sampler::sweep(int accumulate) {
     return GPIRT_B200_OK;
 }
 
+// The un-pipelined sweep as one CUDA graph launch: captured once per value of `accumulate` from the very launch sequence
+// of sweep_eager (same kernels, same order, same draws: the sweep counter reaches the kernels through d_sweep, which
+// the first node of the graph bumps).  At n = 100 a sweep is ~40 kernels of a few microseconds each; the graph removes
+// the per-launch host cost and most of the gaps between dependent kernels.
+int gpirt_b200_sampler::sweep_graph(uint32_t t, int accumulate) {
+    const int a = accumulate ? 1 : 0;
+    if (!gexec[a]) {
+        cudaGraph_t graph = nullptr;
+        const int64_t counted = g_launch_count;   // recording a launch into a graph is not a launch
+        capturing = true;
+        capture_base = t;
+        cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+        int rc = GPIRT_B200_OK;
+        if (e == cudaSuccess) {
+            GP_LAUNCH(k_bump_sweep, 1, 1, 0, stream, d_sweep);
+            rc = sweep_eager(t, accumulate);
+            e = cudaStreamEndCapture(stream, &graph);
+        }
+        capturing = false;
+        g_launch_count = counted;
+        if (rc == GPIRT_B200_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec[a], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != GPIRT_B200_OK || e != cudaSuccess) {   // not capturable on this driver: stay on the eager path for good
+            cudaGetLastError();
+            gexec[a] = nullptr;
+            graph_enabled = false;
+            return sweep_eager(t, accumulate);
+        }
+    }
+    if (d_sweep_value != t - 1) {   // eager sweeps ran in between: resynchronise the device copy of the counter
+        const uint32_t v = t - 1;
+        GP_CUDA(cudaMemcpyAsync(d_sweep, &v, sizeof(v), cudaMemcpyHostToDevice, stream));
+    }
+    GP_CUDA(cudaGraphLaunch(gexec[a], stream));
+    g_launch_count += graph_kernels;   // the kernels inside the graph still launch
+    d_sweep_value = t;
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler::sweep(int accumulate) {
+    const uint32_t t = ++sweep_counter;
+    const bool can_pipe = pipeline && ceil_div(n, CHOL_NB) > 2;
+    // graph replay only for the un-pipelined sweep, without per-step timers, on one GPU, and after one eager sweep has
+    // done every lazy first-use initialisation (function attributes, occupancy queries, the softplus table)
+    if (graph_enabled && !can_pipe && !timing && comm.world <= 1 && warmed && opts.fstar_mode == 0) return sweep_graph(t, accumulate);
+    const int64_t before = g_launch_count;
+    GP_TRY(sweep_eager(t, accumulate));
+    graph_kernels = g_launch_count - before;
+    warmed = true;
+    return GPIRT_B200_OK;
+}
+
 void gpirt_b200_sampler::destroy() {
     if (stream) cudaStreamSynchronize(stream);
+    for (auto& g : gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     flush_timers();
     for (auto e : pool) cudaEventDestroy(e);
     pool.clear();
@@ -715,7 +792,7 @@ void gpirt_b200_sampler::destroy() {
     comm_destroy(comm);
     ti8.destroy();
     dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
-    void* ptrs[] = {work, y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
+    void* ptrs[] = {d_sweep, work, y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
                     kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, chol_flags};
     for (void* p : ptrs) pool_free(p, stream);
     if (stream) cudaStreamSynchronize(stream);
@@ -1192,8 +1269,10 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
         } else {
             GP_LAUNCH(k_f_sd, (unsigned)ceil_div((int64_t)nm, 256), 256, 0, s->stream, gd.f_m2, nm, (double)(n_summarised - 1));
         }
-        if (f_mean_out) GP_CUDA(cudaMemcpyAsync(f_mean_out, gd.f_mean, nm * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        if (f_sd_out) GP_CUDA(cudaMemcpyAsync(f_sd_out, gd.f_m2, nm * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        // fresh pageable destinations: the chunked pinned-bounce copy with host threads, as for the f draws
+        GP_CUDA(cudaStreamSynchronize(s->stream));
+        if (f_mean_out) GP_TRY(chunked_d2h(f_mean_out, gd.f_mean, nm, 0, gd.copy));
+        if (f_sd_out) GP_TRY(chunked_d2h(f_sd_out, gd.f_m2, nm, 1, gd.copy));
     }
     GP_CUDA(cudaStreamSynchronize(s->stream));
     if (cb) cb(100.0, cb_ctx);

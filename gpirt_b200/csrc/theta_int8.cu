@@ -172,6 +172,56 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
 }
 
+// ---- int8 tensor-pipe peak (roofline denominator of the int8 kernels) ---------------------------------------------------
+// One CTA per SM; one elected thread issues `iters` x 4 tcgen05.mma.kind::i8 (M128 N256 K32, both operands from shared
+// memory in the SWIZZLE_128B layout of the real kernels) back to back into two alternating TMEM accumulators, with no
+// loads at all: what the tensor pipe sustains when nothing else limits it.  2 x 128 x 256 x 32 int8 operations per MMA.
+__global__ void __launch_bounds__(128, 1) k_peak_umma_i8(int iters, unsigned* sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + TI_STAGE_BYTES);
+    const uint32_t done = smem_u32(bars);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < TI_STAGE_BYTES / 4; i += 128) ((uint32_t*)smem)[i] = 0x01010101u * (uint32_t)(i & 3);
+    if (tid == 0) {
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy fill above -> async-proxy reads of the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t sa = smem_u32(smem), sb = sa + TI_A_BYTES;
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int k4 = 0; k4 < TI_BK / TI_UMMA_K; ++k4)
+                    umma_i8(tmem_base + (uint32_t)((it & 1) * TI_TMEM_COLS), umma_desc_sw128(sa + k4 * TI_UMMA_K),
+                            umma_desc_sw128(sb + k4 * TI_UMMA_K), (uint32_t)(it > 1 || k4 != 0));
+            }
+            umma_commit(done);
+        }
+    }
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) {   // read one accumulator word so the products are observable
+        uint32_t r;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(tmem_base) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (r == 0xdeadbeefu) sink[blockIdx.x] = r;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
 // ---- operand preparation ----------------------------------------------------------------------------------------------
 // Yt[i][j] (int8, row stride m_pad) from y8[i + j ldy] : 64 x 64 byte tiles through shared memory
 __global__ void __launch_bounds__(256) k_build_yt(const int8_t* __restrict__ y8, int64_t ldy, int n, int m,
@@ -334,6 +384,34 @@ void ThetaInt8::destroy() {
     yt = nullptr; yt_abs = nullptr; Q = nullptr; partial = nullptr; qscale = oscale = nullptr;
     delete maps; maps = nullptr;
     ready = false;
+}
+
+int int8_peak_tops(double* tops) {
+    int dev = 0, sms = 0;
+    GP_CUDA(cudaGetDevice(&dev));
+    GP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int smem = TI_STAGE_BYTES + 1024 + 256, iters = 20000;
+    GP_CUDA(cudaFuncSetAttribute(k_peak_umma_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    unsigned* sink = nullptr;
+    GP_CUDA(cudaMalloc((void**)&sink, (size_t)sms * sizeof(unsigned)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    cudaError_t err = cudaSuccess;
+    for (int r = 0; r < 4 && err == cudaSuccess; ++r) {
+        cudaEventRecord(e0);
+        GP_LAUNCH(k_peak_umma_i8, (unsigned)sms, 128, smem, 0, iters, sink);
+        cudaEventRecord(e1);
+        err = cudaEventSynchronize(e1);
+        float t = 0.f;
+        if (err == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess && r > 0 && t < best) best = t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (err != cudaSuccess) { set_last_error("int8 peak microbenchmark failed: %s", cudaGetErrorString(err)); return GPIRT_B200_ERR_CUDA; }
+    // iters x 4 MMAs of 2 x 128 x 256 x 32 operations per SM
+    if (tops) *tops = (double)sms * iters * 4.0 * 2.0 * TI_BM * TI_BN * TI_UMMA_K / best * 1e-9;
+    return GPIRT_B200_OK;
 }
 
 }  // namespace gpirt

@@ -244,6 +244,13 @@ def fp64_peak_tflops():
     return a.value, b.value
 
 
+def int8_peak_tops():
+    """measured tcgen05.mma.kind::i8 issue-rate peak of the device, 10^12 int8 operations per second"""
+    a = C.c_double(0)
+    _lib.check(_lib.load().gpirt_b200_int8_peak_tops(C.byref(a)))
+    return a.value
+
+
 def rng_probe(seed, sweep, purpose, stream, idx0, count):
     u = np.empty(count); z = np.empty(count)
     _lib.check(_lib.load().gpirt_b200_rng_probe(seed, sweep, purpose, stream, idx0, count, _lib.ptr(u), _lib.ptr(z)))

@@ -39,7 +39,8 @@ typedef struct gpirt_b200_opts {
     int32_t fstar_mode;   /* 0: mean_j = (S^-1 K*)^T f_j (two n x 1001 triangular solves per sweep);
                              1: literal per-item alpha_j = L^-T L^-1 f_j (draw-fstar.cpp:3-8,24) */
     int32_t skip_f_draws; /* 1: do not store f draws (f_out may be NULL); reference behaviour is 0 */
-    int32_t use_graph;    /* reserved */
+    int32_t use_graph;    /* 0 (default): small problems (un-pipelined sweep, n <= 256) replay each sweep as one CUDA graph launch;
+                             -1: never (every kernel launched individually); draws are identical either way */
     /* item sharding across GPUs (one process per GPU).  world_size <= 1: single GPU, fields ignored. */
     int32_t rank, world_size;
     int64_t m_global;     /* total items over all ranks */
@@ -168,6 +169,9 @@ int gpirt_b200_trsm_lower(int trans, int64_t n, int64_t nrhs, const double* L, d
 int gpirt_b200_ll_bar(const double* f, const double* y, const double* mu, int64_t n, int64_t m, double* out);
 /* FP64 tensor-pipe peak of the current device, TFLOP/s (DMMA.8x8x4 issue-rate microbenchmark; roofline denominator) */
 int gpirt_b200_fp64_peak_tflops(double* dmma_tflops, double* dfma_tflops);
+/* int8 tensor-pipe peak of the current device in 10^12 operations/s: tcgen05.mma.kind::i8 (M128 N256 K32, operands in
+ * shared memory) issued back to back on every SM with no loads (roofline denominator of the int8 kernels) */
+int gpirt_b200_int8_peak_tops(double* tops);
 /* device-side Philox variates by address (tests: must equal the oracle's gpo_keyed_* bit-for-bit / to 1 ulp) */
 int gpirt_b200_rng_probe(uint64_t seed, uint32_t sweep, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
                          double* uniforms, double* normals);

@@ -25,8 +25,8 @@ uid = bytes(uid_t.cpu().tolist())
 n, m, S, B = int(os.environ.get("SHARD_N", "300")), int(os.environ.get("SHARD_M", "90")), 3, 2
 missing = float(os.environ.get("SHARD_MISSING", "0.05"))
 p = make_problem(n, m, seed=5, missing=missing)
-per = (m + world - 1) // world
-j0, j1 = rank * per, min(m, (rank + 1) * per)
+from gpirt_b200.sharding import item_block
+j0, j1 = item_block(m, rank, world)
 got = G.gpirtMCMC(ResponseMatrix(p["y"][:, j0:j1]), S, B, beta_prior_means=p["pm"][:, j0:j1], beta_prior_sds=p["psd"][:, j0:j1],
                   beta_proposal_sds=p["pstep"][:, j0:j1], theta_init=p["theta"], seed=99, device=local,
                   shard=(rank, world, m, j0, uid))
