@@ -239,15 +239,16 @@ __global__ void k_scatter_block_inverses(const double* __restrict__ Dinv, int64_
 }
 
 int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv, int64_t ldd, double* X,
-                int64_t ldx, double* T, int64_t ldt) {
+                int64_t ldx, double* T, int64_t ldt, int max_block) {
     if (n <= 0) return GPIRT_B200_OK;
+    const int64_t stop = max_block > 0 ? std::min<int64_t>(n, max_block) : n;
     GP_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * n * sizeof(double), stream));
     {
         dim3 grid((unsigned)n, (unsigned)ceil_div(n, 128));
         GP_LAUNCH(k_scatter_block_inverses, grid, 128, 0, stream, Dinv, ldd, n, X, ldx);
         GP_CUDA(cudaGetLastError());
     }
-    for (int64_t s = CHOL_NB; s < n; s *= 2) {
+    for (int64_t s = CHOL_NB; s < stop; s *= 2) {
         const int full_pairs = (int)(n / (2 * s));           // pairs whose second block is complete
         const int64_t o_r = (int64_t)full_pairs * 2 * s;     // offset of a possible ragged pair
         const int s2 = (int)std::min<int64_t>(s, n - (o_r + s));   // size of its second block (<= 0: none)

@@ -35,8 +35,9 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
 
 // X = L^-1 (n x n, lower; strict upper zero) by batched recursive doubling from the 128 x 128 block inverses:
 //   inv([[L11,0],[L21,L22]]) = [[X11,0],[-X22 L21 X11, X22]], all pairs of one level in a single batched GEMM launch.
-// T is n x n scratch.
+// T is n x n scratch.  max_block > 0 (a power-of-two multiple of 128) stops the doubling there: X then holds the inverses of
+// the max_block x max_block diagonal blocks of L only (zeros elsewhere) — the leaf blocks of a coarser substitution.
 int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv128, int64_t ldd, double* X,
-                int64_t ldx, double* T, int64_t ldt);
+                int64_t ldx, double* T, int64_t ldt, int max_block = 0);
 
 }  // namespace gpirt

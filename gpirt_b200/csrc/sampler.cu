@@ -430,6 +430,9 @@ int gpirt_b200_sampler::trsm_fwd_step(cudaStream_t st, int k) {
     return GPIRT_B200_OK;
 }
 // s from tmp = L^-1 K* (:20), then the backward substitution  L^T A = tmp  (tmp = kstar2 is consumed, A -> kstar)    :24
+// The backward pass cannot trail the factorisation (it starts at the last block), so it is the serial tail of the sharded
+// sweep: instead of 32 steps with the 128-blocks it runs with the inverses of 1024 x 1024 diagonal blocks (built from the
+// 128-block inverses by three levels of batched recursive doubling, ~3 GFLOP) — 4 steps of two large products each.
 int gpirt_b200_sampler::trsm_bwd(cudaStream_t st) {
     int c0, nc;
     grid_slice(c0, nc);
@@ -437,10 +440,19 @@ int gpirt_b200_sampler::trsm_bwd(cudaStream_t st) {
     double* A = kstar + (int64_t)c0 * ldn;
     double* Y = kstar2 + (int64_t)c0 * ldn;
     GP_TRY(launch_fstar_sd(st, Y, ldn, n, nc, s + c0));
-    const int nblk = (int)ceil_div(n, CHOL_NB);
+    static const int forced = getenv("GPIRT_BWD_BLOCK") ? atoi(getenv("GPIRT_BWD_BLOCK")) : 0;
+    int blk = forced > 0 ? forced : (n >= 2048 ? 1024 : (n >= 1024 ? 512 : CHOL_NB));
+    if (blk % CHOL_NB != 0 || (blk & (blk - 1)) != 0) blk = CHOL_NB;
+    const double* Xb = Dinv;       // leaf inverses: block k at rows k * blk of an n x blk array ...
+    int64_t ldx = ldn, diag_step = 0;
+    if (blk > CHOL_NB) {           // ... or on the diagonal of Linv (n x n)
+        GP_TRY(trtri_lower(st, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn, blk));
+        Xb = Linv; diag_step = ldn;
+    }
+    const int nblk = (int)ceil_div(n, blk);
     for (int k = nblk - 1; k >= 0; --k) {
-        const int r0 = k * CHOL_NB, nb = std::min(CHOL_NB, n - r0);
-        GP_TRY(gemm_f64(st, true, false, G(nb, nc, nb, Dinv + r0, ldn, Y + r0, ldn, A + r0, ldn, 1.0, 0.0, TRI_A_UPPER)));
+        const int r0 = k * blk, nb = std::min(blk, n - r0);
+        GP_TRY(gemm_f64(st, true, false, G(nb, nc, nb, Xb + r0 + (int64_t)r0 * diag_step, ldx, Y + r0, ldn, A + r0, ldn, 1.0, 0.0, TRI_A_UPPER)));
         if (r0 > 0)
             GP_TRY(gemm_f64(st, true, false, G(r0, nc, nb, L + r0, ldn, A + r0, ldn, Y, ldn, -1.0, 1.0, TRI_NONE)));
     }
@@ -650,6 +662,7 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         toc_on(a, st_trsm);
     }
     bool first = true;
+    int lz_slice = 0, lz_prev_end = 0, lz_next_end = lz_group;
     lookahead.after_panel = [&](int k, int nblk, cudaEvent_t done) -> int {
         if (trsm_route) {   // forward substitution step k trails panel k
             GP_CUDA(cudaStreamWaitEvent(st_trsm, done, 0));
@@ -657,9 +670,14 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
             GP_TRY(trsm_fwd_step(st_trsm, k));
             toc_on(sg, st_trsm);
         }
-        if ((k + 1) % lz_group != 0 && k != nblk - 1) return GPIRT_B200_OK;
-        const int g = k / lz_group;
-        const int r0 = g * lz_group * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
+        // a slice of the product ends after every lz_group panels.  (Shrinking the later slices geometrically so that less of
+        // the product is left when the factorisation ends was measured and lost: every slice pays the fixed-point kernel's
+        // epilogue over all row tiles below it, 9.4 -> 10.3 ms per sweep at C3.)
+        if (k + 1 != lz_next_end && k != nblk - 1) return GPIRT_B200_OK;
+        const int g = lz_slice++;
+        const int r0 = lz_prev_end * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
+        lz_prev_end = k + 1;
+        lz_next_end = min(nblk, lz_prev_end + lz_group);
         if (first) {
             GP_CUDA(cudaStreamWaitEvent(st_lz, ev_z, 0));
             first = false;

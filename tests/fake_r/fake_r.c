@@ -1,6 +1,6 @@
 /* TEST INFRASTRUCTURE: minimal R runtime stand-in + a harness that loads the shim the way R would
  * (R_init_gpirt -> registered .Call routine with 7 arguments) and calls it on a small problem read from a file.
- *   fake_r_harness <in.bin> <out.bin>
+ *   fake_r_harness <in.bin> <out.bin> [thin]      (thin > 0: the extended routine _gpirt_gpirtMCMC_b200, arity 10)
  * in.bin : int32 n, m, S, B; uint64 rng_state; double y[n*m], theta[n], pm[2m], psd[2m], pstep[2m]
  * out.bin: uint64 seed_used; theta (S+1)*n, beta 2*m*(S+1), f n*m*(S+1), IRFs 1001*m   (doubles)
  * exit code 0 ok, 3 = Rf_error was raised (message on stderr), 2 = registration problem */
@@ -57,6 +57,9 @@ void Rf_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); fprintf(stderr, "Error: "); vfprintf(stderr, fmt, ap); fprintf(stderr, "\n"); va_end(ap);
     longjmp(error_jmp, 1);
 }
+void Rf_warning(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); fprintf(stderr, "Warning: "); vfprintf(stderr, fmt, ap); fprintf(stderr, "\n"); va_end(ap);
+}
 void Rf_onintr(void) { fprintf(stderr, "Interrupted\n"); longjmp(error_jmp, 2); }
 void Rprintf(const char* fmt, ...) { if (quiet) return; va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap); }
 void GetRNGstate(void) { rng_open = 1; }
@@ -75,16 +78,22 @@ int R_useDynamicSymbols(DllInfo* d, int v) { d->dynamic_symbols = v; return 1; }
 
 void R_init_gpirt(DllInfo*);
 typedef SEXP (*call7)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*call10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 int main(int argc, char** argv) {
     the_dll.dynamic_symbols = 1;
     R_init_gpirt(&the_dll);   /* what dyn.load() does for useDynLib(gpirt, .registration = TRUE) */
     if (!the_dll.call_methods || the_dll.dynamic_symbols != 0) return 2;
-    const R_CallMethodDef* def = NULL;
+    const R_CallMethodDef *def = NULL, *ext = NULL;
     int count = 0;
-    for (const R_CallMethodDef* p = the_dll.call_methods; p->name; ++p) { ++count; if (!strcmp(p->name, "_gpirt_gpirtMCMC")) def = p; }
-    if (!def || def->numArgs != 7 || count != 1) return 2;
-    if (argc < 3) { printf("registered %s arity %d\n", def->name, def->numArgs); return 0; }
+    for (const R_CallMethodDef* p = the_dll.call_methods; p->name; ++p) {
+        ++count;
+        if (!strcmp(p->name, "_gpirt_gpirtMCMC")) def = p;
+        if (!strcmp(p->name, "_gpirt_gpirtMCMC_b200")) ext = p;
+    }
+    if (!def || def->numArgs != 7 || !ext || ext->numArgs != 10 || count != 2) return 2;
+    if (argc < 3) { printf("registered %s arity %d\nregistered %s arity %d\n", def->name, def->numArgs, ext->name, ext->numArgs); return 0; }
+    const int thin = argc > 3 ? atoi(argv[3]) : 0;   /* > 0: call the extended routine with thin, store_f = TRUE, f_summary = TRUE */
     FILE* in = fopen(argv[1], "rb");
     if (!in) return 5;
     int hdr[4];
@@ -104,17 +113,30 @@ int main(int argc, char** argv) {
     rng_state = st;
     int jc = setjmp(error_jmp);
     if (jc) return 3;
-    SEXP res = ((call7)def->fun)(y, theta, sS, sB, pm, psd, pstep);
-    if (res->type != VECSXP || res->length != 4 || !res->names) return 6;
-    const char* want[4] = {"theta", "beta", "f", "IRFs"};
-    for (int i = 0; i < 4; ++i) if (strcmp(CHAR(VECTOR_ELT(res->names, i)), want[i])) return 6;
+    SEXP res;
+    if (thin > 0) {
+        SEXP sT = Rf_allocVector(REALSXP, 1), sF = Rf_allocVector(INTSXP, 1), sM = Rf_allocVector(INTSXP, 1);
+        REAL(sT)[0] = thin; INTEGER(sF)[0] = 1; INTEGER(sM)[0] = 1;
+        res = ((call10)ext->fun)(y, theta, sS, sB, pm, psd, pstep, sT, sF, sM);
+    } else {
+        res = ((call7)def->fun)(y, theta, sS, sB, pm, psd, pstep);
+    }
+    const int len = thin > 0 ? 6 : 4, slots = thin > 0 ? S / thin + 1 : S + 1;
+    if (res->type != VECSXP || res->length != len || !res->names) return 6;
+    const char* want[6] = {"theta", "beta", "f", "IRFs", "f_mean", "f_sd"};
+    for (int i = 0; i < len; ++i) if (strcmp(CHAR(VECTOR_ELT(res->names, i)), want[i])) return 6;
     SEXP th = VECTOR_ELT(res, 0), be = VECTOR_ELT(res, 1), f = VECTOR_ELT(res, 2), irf = VECTOR_ELT(res, 3);
-    if (th->dims[0] != S + 1 || th->dims[1] != n || be->ndim != 3 || be->dims[0] != 2 || be->dims[1] != m || be->dims[2] != S + 1 ||
-        f->dims[0] != n || f->dims[1] != m || f->dims[2] != S + 1 || irf->dims[0] != 1001 || irf->dims[1] != m) return 7;
+    if (th->dims[0] != slots || th->dims[1] != n || be->ndim != 3 || be->dims[0] != 2 || be->dims[1] != m || be->dims[2] != slots ||
+        f->dims[0] != n || f->dims[1] != m || f->dims[2] != slots || irf->dims[0] != 1001 || irf->dims[1] != m) return 7;
     FILE* out = fopen(argv[2], "wb");
     fwrite(&seed, sizeof(seed), 1, out);
     fwrite(REAL(th), 8, (size_t)th->length, out); fwrite(REAL(be), 8, (size_t)be->length, out);
     fwrite(REAL(f), 8, (size_t)f->length, out); fwrite(REAL(irf), 8, (size_t)irf->length, out);
+    if (thin > 0) {
+        SEXP fm = VECTOR_ELT(res, 4), fsd = VECTOR_ELT(res, 5);
+        if (fm->dims[0] != n || fm->dims[1] != m || fsd->dims[0] != n || fsd->dims[1] != m) return 7;
+        fwrite(REAL(fm), 8, (size_t)fm->length, out); fwrite(REAL(fsd), 8, (size_t)fsd->length, out);
+    }
     fclose(out);
     return 0;
 }

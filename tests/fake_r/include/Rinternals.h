@@ -47,6 +47,7 @@ SEXP VECTOR_ELT(SEXP, R_xlen_t);
 void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
 const char* CHAR(SEXP);
 void Rf_error(const char*, ...) __attribute__((noreturn));
+void Rf_warning(const char*, ...);
 void Rf_onintr(void);
 #ifdef __cplusplus
 }

@@ -351,11 +351,12 @@ def test_chain_fixed_point_products_match_dmma_products(G, monkeypatch):
     assert np.max(np.abs(a["IRFs"] - b["IRFs"])) <= 1e-9
 
 
-@pytest.mark.parametrize("n,m", [(100, 40), (400, 150), (700, 320)])
+@pytest.mark.parametrize("n,m", [(100, 40), (400, 150), (700, 320), (1100, 260), (2304, 260)])
 def test_chain_blocked_substitution_solves_match_inverse_route(G, O, n, m, monkeypatch):
     """GPIRT_SOLVE_MODE=1 (the default when items are sharded over GPUs): L^-1 K* and L^-T(.) by blocked substitution
     with the 128-block inverses, forward steps trailing the Cholesky panels, instead of L^-1 + triangular products
-    (draw-fstar.cpp:19,24).  Same chain as the inverse route, and in lock-step with the oracle."""
+    (draw-fstar.cpp:19,24).  Same chain as the inverse route, and in lock-step with the oracle.  n >= 1024: the backward
+    pass runs on 512 / 1024-wide diagonal-block inverses (n = 2304: two full 1024-blocks and a ragged one)."""
     from gpirt_b200 import ResponseMatrix
     prob = make_problem(n, m, seed=n + 5, missing=0.04)
     out = {}

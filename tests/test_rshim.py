@@ -29,11 +29,13 @@ def write_input(path, p, S, B, rng_state):
             fh.write(np.asfortranarray(a, dtype=np.float64).tobytes(order="F"))
 
 
-def test_shim_registers_one_call_routine_with_arity_7():
+def test_shim_registers_the_reference_routine_with_arity_7():
+    """R_init_gpirt registers _gpirt_gpirtMCMC with 7 arguments exactly as src/RcppExports.cpp:32-40 does (dynamic symbols
+    off); the only other routine is the same call with the draw-storage options as three trailing arguments"""
     build_harness()
     out = subprocess.run([HARNESS], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
-    assert out.stdout.strip() == "registered _gpirt_gpirtMCMC arity 7"
+    assert out.stdout.split("\n")[:2] == ["registered _gpirt_gpirtMCMC arity 7", "registered _gpirt_gpirtMCMC_b200 arity 10"]
 
 
 def test_shim_raises_r_error_without_gpu(tmp_path):
@@ -69,3 +71,30 @@ def test_shim_call_matches_c_abi(tmp_path):
     assert np.array_equal(be.reshape((2, m, S + 1), order="F"), got["beta"])
     assert np.array_equal(f.reshape((n, m, S + 1), order="F"), got["f"])
     assert np.array_equal(irf.reshape((1001, m), order="F"), got["IRFs"])
+
+
+@pytest.mark.gpu
+def test_shim_extended_call_thins_and_summarises(tmp_path):
+    """.Call(`_gpirt_gpirtMCMC_b200`, ..., thin, store_f, f_summary): list of 6 with 1 + S %/% thin slots"""
+    import gpirt_b200
+    import gpirt_b200.sampler as G
+    build_harness()
+    n, m, S, B, thin = 40, 13, 9, 2, 3
+    p = make_problem(n, m, seed=4, missing=0.05)
+    write_input(tmp_path / "in.bin", p, S, B, 777)
+    out = subprocess.run([HARNESS, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(thin)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    seed = struct.unpack("<Q", raw[:8])[0]
+    vals = np.frombuffer(raw[8:], dtype=np.float64)
+    slots = S // thin + 1
+    sizes = [slots * n, 2 * m * slots, n * m * slots, 1001 * m, n * m, n * m]
+    assert vals.size == sum(sizes)
+    th, be, f, irf, fm, fsd = np.split(vals, np.cumsum(sizes)[:-1])
+    got = G.gpirtMCMC(gpirt_b200.ResponseMatrix(p["y"]), S, B, beta_prior_means=p["pm"], beta_prior_sds=p["psd"],
+                      beta_proposal_sds=p["pstep"], theta_init=p["theta"], seed=seed, thin=thin, f_summary=True)
+    assert np.array_equal(th.reshape((slots, n), order="F"), got["theta"])
+    assert np.array_equal(f.reshape((n, m, slots), order="F"), got["f"])
+    assert np.array_equal(irf.reshape((1001, m), order="F"), got["IRFs"])
+    assert np.array_equal(fm.reshape((n, m), order="F"), got["f_mean"])
+    assert np.array_equal(fsd.reshape((n, m), order="F"), got["f_sd"])
