@@ -26,8 +26,15 @@ def test_call_stubs_match_the_registered_routines():
     assert registered == {"_gpirt_gpirtMCMC": 7, "_gpirt_gpirtMCMC_b200": 10}
     for f in ("RcppExports.R", "gpirtMCMC_b200.R"):
         src = open(os.path.join(RPKG, "R", f)).read()
-        for name, args in re.findall(r"\.Call\(`(_gpirt_\w+)`,([^)]*)\)", src, re.S):
-            assert registered[name] == len([a for a in args.split(",") if a.strip()]), (f, name)
+        for mt in re.finditer(r"\.Call\(`(_gpirt_\w+)`,", src):
+            depth, nargs, i = 1, 1, mt.end()
+            while depth:                       # count the top-level commas up to the matching parenthesis
+                c = src[i]
+                depth += c == "("
+                depth -= c == ")"
+                nargs += c == "," and depth == 1
+                i += 1
+            assert registered[mt.group(1)] == nargs, (f, mt.group(1), nargs)
     ns = open(os.path.join(RPKG, "NAMESPACE")).read()
     directives = [ln for ln in ns.splitlines() if ln.strip() and not ln.startswith("#")]
     assert "useDynLib(gpirt, .registration = TRUE)" in directives and not any("Rcpp" in ln for ln in directives)
