@@ -1,6 +1,8 @@
 // Single-operation entry points on HOST buffers (each replaces one reference function; the parity tests call these)
 // and the FP64 peak microbenchmark used as the tensor-roofline denominator.
 #include <vector>
+#include <algorithm>
+#include <cmath>
 
 #include <climits>
 
@@ -225,6 +227,96 @@ int gpirt_b200_fp64_peak_tflops(double* dmma_tflops, double* dfma_tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (dmma_tflops) *dmma_tflops = (double)blocks * (threads / 32) * iters * 8 * 512.0 / best_m * 1e-9;
     if (dfma_tflops) *dfma_tflops = (double)blocks * threads * (double)iters * 8 * 2.0 / best_f * 1e-9;
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_response_matrix(const double* codes, int64_t n, int64_t m, const double* yea, int n_yea, const double* nay,
+                               int n_nay, const double* missing, int n_missing, double* y_out, int64_t* kept, int64_t* m_kept,
+                               int64_t* n_uncoded) {
+    if (!codes || !y_out || !kept || !m_kept || n < 0 || m < 0 || n_yea < 0 || n_nay < 0 || n_missing < 0 ||
+        (n_yea && !yea) || (n_nay && !nay) || (n_missing && !missing) || n > INT_MAX || m > INT_MAX)
+        return GPIRT_B200_ERR_ARG;
+    GP_TRY(have_device());
+    *m_kept = 0;
+    if (n_uncoded) *n_uncoded = 0;
+    if (n == 0 || m == 0) return GPIRT_B200_OK;
+    DevBuf dc, dy, dout, dlists, dflags, dkept, dcount;
+    GP_TRY(dc.alloc((size_t)n * m)); GP_TRY(dy.alloc((size_t)n * m)); GP_TRY(dlists.alloc((size_t)n_yea + n_nay + n_missing + 1));
+    GP_TRY(dflags.alloc((size_t)m / 2 + 1)); GP_TRY(dkept.alloc((size_t)m)); GP_TRY(dcount.alloc(1));
+    GP_CUDA(cudaMemcpy(dc.p, codes, (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_yea) GP_CUDA(cudaMemcpy(dlists.p, yea, n_yea * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_nay) GP_CUDA(cudaMemcpy(dlists.p + n_yea, nay, n_nay * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_missing) GP_CUDA(cudaMemcpy(dlists.p + n_yea + n_nay, missing, n_missing * sizeof(double), cudaMemcpyHostToDevice));
+    GP_CUDA(cudaMemset(dcount.p, 0, sizeof(double)));
+    int* flags = reinterpret_cast<int*>(dflags.p);
+    GP_TRY(launch_response_code(0, dc.p, (int)n, (int)m, dlists.p, n_yea, dlists.p + n_yea, n_nay, dlists.p + n_yea + n_nay, n_missing,
+                                dy.p, flags, reinterpret_cast<unsigned long long*>(dcount.p)));
+    std::vector<int> h((size_t)m);
+    unsigned long long unc = 0;
+    GP_CUDA(cudaMemcpy(h.data(), flags, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost));
+    GP_CUDA(cudaMemcpy(&unc, dcount.p, sizeof(unc), cudaMemcpyDeviceToHost));
+    if (n_uncoded) *n_uncoded = (int64_t)unc;
+    int64_t mk = 0;
+    for (int64_t j = 0; j < m; ++j) if (!h[(size_t)j]) kept[mk++] = j;       // unanimous items are discarded (:80-88)
+    *m_kept = mk;
+    if (mk == 0) return GPIRT_B200_OK;
+    GP_TRY(dout.alloc((size_t)n * mk));
+    GP_CUDA(cudaMemcpy(dkept.p, kept, (size_t)mk * sizeof(int64_t), cudaMemcpyHostToDevice));
+    GP_TRY(launch_gather_columns(0, dy.p, (int)n, reinterpret_cast<const int64_t*>(dkept.p), (int)mk, dout.p));
+    GP_CUDA(cudaMemcpy(y_out, dout.p, (size_t)n * mk * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPIRT_B200_OK;
+}
+
+// Geyer initial-monotone-sequence ESS of one chain (draws x) and the pieces split-R-hat needs
+static double chain_ess(const double* x, int64_t T) {
+    double mean = 0.0;
+    for (int64_t t = 0; t < T; ++t) mean += x[t];
+    mean /= (double)T;
+    auto acov = [&](int64_t lag) { double a = 0.0; for (int64_t t = 0; t + lag < T; ++t) a += (x[t] - mean) * (x[t + lag] - mean); return a / (double)T; };
+    const double c0 = acov(0);
+    if (!(c0 > 0.0)) return NAN;                      // constant chain
+    double sum = 0.0, prev = INFINITY;
+    for (int64_t k = 0; 2 * k + 1 < T; ++k) {
+        double pair = (acov(2 * k) + acov(2 * k + 1)) / c0;
+        if (pair <= 0.0) break;
+        pair = std::min(pair, prev);                  // initial monotone sequence
+        prev = pair;
+        sum += pair;
+    }
+    const double tau = -1.0 + 2.0 * sum;
+    return (double)T / std::max(tau, 1e-12);
+}
+
+int gpirt_b200_theta_diagnostics(const double* theta_draws, int64_t draws, int64_t n, int chains, double* rhat, double* ess) {
+    if (!theta_draws || draws < 4 || n < 0 || chains < 1 || (!rhat && !ess)) return GPIRT_B200_ERR_ARG;
+    const int64_t half = draws / 2;                   // split-R-hat: every chain contributes its two halves
+    std::vector<double> col((size_t)draws);
+    for (int64_t i = 0; i < n; ++i) {
+        double W = 0.0, grand = 0.0, ess_sum = 0.0;
+        std::vector<double> means;
+        for (int c = 0; c < chains; ++c) {
+            const double* x = theta_draws + (size_t)c * draws * n + (size_t)i * draws;   // chain c: draws x n, column-major
+            for (int h = 0; h < 2; ++h) {
+                const double* seg = x + (h ? draws - half : 0);
+                double mu = 0.0, v = 0.0;
+                for (int64_t t = 0; t < half; ++t) mu += seg[t];
+                mu /= (double)half;
+                for (int64_t t = 0; t < half; ++t) v += (seg[t] - mu) * (seg[t] - mu);
+                W += v / (double)(half - 1);
+                means.push_back(mu);
+                grand += mu;
+            }
+            if (ess) ess_sum += chain_ess(x, draws);
+        }
+        const double M = (double)means.size();
+        W /= M; grand /= M;
+        double Bv = 0.0;
+        for (double mu : means) Bv += (mu - grand) * (mu - grand);
+        Bv *= (double)half / (M - 1.0);
+        const double var_plus = ((double)(half - 1) / (double)half) * W + Bv / (double)half;
+        if (rhat) rhat[i] = W > 0.0 ? std::sqrt(var_plus / W) : NAN;
+        if (ess) ess[i] = ess_sum;
+    }
     return GPIRT_B200_OK;
 }
 

@@ -881,3 +881,61 @@ int launch_ll_bar(cudaStream_t st, const double* f, const double* y, const doubl
 }
 
 }  // namespace gpirt
+
+// ------------------------------------------------------------------------------------------------------------------
+// Response coding on the device (reference R/response_matrix.R:79-98, numeric codes): yea -> +1, nay -> -1, everything
+// else (missing codes, NA, codes nobody listed) -> NA, later rules winning on overlapping codes (yea, then nay, then
+// missing, as the reference assigns them).  One CTA per item; it also reports whether the item is unanimous
+// (length(unique(na.omit(x))) == 1: exactly one of {+1, -1} occurs) and how many cells had no code at all.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gpirt {
+
+__global__ void __launch_bounds__(256) k_response_code(const double* __restrict__ codes, int n, const double* __restrict__ yea,
+                                                       int n_yea, const double* __restrict__ nay, int n_nay,
+                                                       const double* __restrict__ mis, int n_mis, double* __restrict__ y,
+                                                       int* __restrict__ unanimous, unsigned long long* __restrict__ n_uncoded) {
+    __shared__ int s_flags;
+    const int j = blockIdx.x;
+    if (threadIdx.x == 0) s_flags = 0;
+    __syncthreads();
+    int flags = 0;
+    unsigned long long uncoded = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = codes[i + (int64_t)j * n];
+        double out = nan("");
+        bool known = isnan(v);                         // NA is always missing
+        for (int k = 0; k < n_yea; ++k) if (v == yea[k]) { out = 1.0; known = true; }
+        for (int k = 0; k < n_nay; ++k) if (v == nay[k]) { out = -1.0; known = true; }
+        for (int k = 0; k < n_mis; ++k) if (v == mis[k]) { out = nan(""); known = true; }
+        if (!known) ++uncoded;
+        if (out == 1.0) flags |= 1; else if (out == -1.0) flags |= 2;
+        y[i + (int64_t)j * n] = out;
+    }
+    if (flags) atomicOr(&s_flags, flags);
+    if (uncoded) atomicAdd(n_uncoded, uncoded);
+    __syncthreads();
+    if (threadIdx.x == 0) unanimous[j] = (s_flags == 1 || s_flags == 2) ? 1 : 0;
+}
+// compaction of the kept items: out[:, c] = y[:, kept[c]]
+__global__ void __launch_bounds__(256) k_gather_columns(const double* __restrict__ y, int n, const int64_t* __restrict__ kept,
+                                                        double* __restrict__ out) {
+    const int i = blockIdx.y * blockDim.x + threadIdx.x, c = blockIdx.x;
+    if (i < n) out[i + (int64_t)c * n] = y[i + kept[c] * (int64_t)n];
+}
+
+int launch_response_code(cudaStream_t st, const double* codes, int n, int m, const double* yea, int n_yea, const double* nay,
+                         int n_nay, const double* mis, int n_mis, double* y, int* unanimous, unsigned long long* n_uncoded) {
+    if (n <= 0 || m <= 0) return GPIRT_B200_OK;
+    GP_LAUNCH(k_response_code, (unsigned)m, 256, 0, st, codes, n, yea, n_yea, nay, n_nay, mis, n_mis, y, unanimous, n_uncoded);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+int launch_gather_columns(cudaStream_t st, const double* y, int n, const int64_t* kept, int m_kept, double* out) {
+    if (n <= 0 || m_kept <= 0) return GPIRT_B200_OK;
+    dim3 grid((unsigned)m_kept, (unsigned)ceil_div(n, 256));
+    GP_LAUNCH(k_gather_columns, grid, 256, 0, st, y, n, kept, out);
+    GP_CUDA(cudaGetLastError());
+    return GPIRT_B200_OK;
+}
+
+}  // namespace gpirt

@@ -51,6 +51,10 @@ int launch_beta(cudaStream_t st, double* beta, const double* f, int64_t ld, cons
 int launch_ll_bar(cudaStream_t st, const double* f, const double* y, const double* mu, int n, int m, double* out);
 // IRF = plogis(sum / S)
 int launch_irf_finish(cudaStream_t st, const double* irf_sum, int64_t ld, int N, int m, double inv_samples, double* out);
+// response coding (R/response_matrix.R:79-98, numeric codes) and compaction of the kept items
+int launch_response_code(cudaStream_t st, const double* codes, int n, int m, const double* yea, int n_yea, const double* nay,
+                         int n_nay, const double* mis, int n_mis, double* y, int* unanimous, unsigned long long* n_uncoded);
+int launch_gather_columns(cudaStream_t st, const double* y, int n, const int64_t* kept, int m_kept, double* out);
 int launch_rng_probe(cudaStream_t st, RngKey key, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
                      double* uniforms, double* normals);
 

@@ -244,6 +244,31 @@ def fp64_peak_tflops():
     return a.value, b.value
 
 
+def response_matrix_native(codes, yea=(1, 2, 3), nay=(4, 5, 6), missing=(0, 7, 8, 9)):
+    """Numeric response codes -> (y n x m_kept in {+1,-1,NaN}, kept column indices, number of uncoded cells), coded and
+    filtered on the device (the numeric case of R/response_matrix.R:79-98; NaN in `codes` is NA)."""
+    codes = _F(codes)
+    n, m = codes.shape
+    lists = [np.ascontiguousarray(v, dtype=np.float64) for v in (yea, nay, missing)]
+    y = np.empty((n, m), order="F")
+    kept = np.zeros(m, dtype=np.int64)
+    mk, unc = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.load().gpirt_b200_response_matrix(
+        _lib.ptr(codes), n, m, _lib.ptr(lists[0]), lists[0].size, _lib.ptr(lists[1]), lists[1].size, _lib.ptr(lists[2]), lists[2].size,
+        _lib.ptr(y), kept.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mk), C.byref(unc)))
+    return np.asfortranarray(y[:, :mk.value]), kept[:mk.value].copy(), unc.value
+
+
+def theta_diagnostics(theta_chains):
+    """theta_chains: list of (draws, n) arrays (one per chain, initial row removed) -> (split-R-hat, ESS) per respondent"""
+    chains = [np.asfortranarray(np.asarray(c, dtype=np.float64)) for c in theta_chains]
+    draws, n = chains[0].shape
+    buf = np.concatenate([c.ravel(order="F") for c in chains])
+    rhat = np.empty(n); ess = np.empty(n)
+    _lib.check(_lib.load().gpirt_b200_theta_diagnostics(_lib.ptr(buf), draws, n, len(chains), _lib.ptr(rhat), _lib.ptr(ess)))
+    return rhat, ess
+
+
 def int8_peak_tops():
     """measured tcgen05.mma.kind::i8 issue-rate peak of the device, 10^12 int8 operations per second"""
     a = C.c_double(0)

@@ -172,6 +172,19 @@ int gpirt_b200_fp64_peak_tflops(double* dmma_tflops, double* dfma_tflops);
 /* int8 tensor-pipe peak of the current device in 10^12 operations/s: tcgen05.mma.kind::i8 (M128 N256 K32, operands in
  * shared memory) issued back to back on every SM with no loads (roofline denominator of the int8 kernels) */
 int gpirt_b200_int8_peak_tops(double* tops);
+/* ---- the host steps either side of the sampler ---- */
+/* Response coding, the producer of y (reference R/response_matrix.R:79-98) for numeric code matrices, on the device:
+ * codes n x m (column-major doubles, NaN = NA); yea / nay / missing code lists; cells with a code in none of the lists are
+ * treated as missing and counted in n_uncoded (the reference warns about them).  y_out (n x m, the first *m_kept columns
+ * are written) receives exactly {+1, -1, NaN}; unanimous items (one distinct non-missing value) are discarded; kept[c]
+ * is the original column of output column c. */
+int gpirt_b200_response_matrix(const double* codes, int64_t n, int64_t m, const double* yea, int n_yea, const double* nay,
+                               int n_nay, const double* missing, int n_missing, double* y_out, int64_t* kept, int64_t* m_kept,
+                               int64_t* n_uncoded);
+/* Multi-chain diagnostics of theta draws: theta_draws holds `chains` blocks of draws x n (column-major, as the theta
+ * output without its first row); per respondent the split-R-hat over the 2 x chains half-chains (rhat, optional) and the
+ * summed effective sample size, Geyer's initial monotone sequence estimator per chain (ess, optional). */
+int gpirt_b200_theta_diagnostics(const double* theta_draws, int64_t draws, int64_t n, int chains, double* rhat, double* ess);
 /* device-side Philox variates by address (tests: must equal the oracle's gpo_keyed_* bit-for-bit / to 1 ulp) */
 int gpirt_b200_rng_probe(uint64_t seed, uint32_t sweep, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
                          double* uniforms, double* normals);
