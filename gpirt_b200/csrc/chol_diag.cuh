@@ -37,12 +37,12 @@ constexpr int DLD = DB + 4;          // 132
 constexpr int NBK = 32;              // inner panel width
 constexpr int NPAN = DB / NBK;       // 4
 constexpr int DWARPS = 8, DTHREADS = DWARPS * 32;
-constexpr int SCALER_WARP = DWARPS - 1;
+constexpr int SCALER_WARP = DWARPS - 1;   // warp 4 shares its scheduler with the leader and stays idle during the panels
 
 struct __align__(16) Smem {
     double S[DB * DLD];              // element (r, c) at S[c * DLD + r]
-    double colbuf[NBK * NBK];        // column c of the current panel's diagonal block, unscaled: colbuf[c * 32 + row]
-    double pbuf[2 * NBK];            // (pivot_c, 1 / pivot_c)
+    double2 pairbuf[(NBK / 2) * NBK];   // columns (c, c+1) of the current panel's diagonal block, unscaled: pairbuf[pair * 32 + row]
+    double pbuf[(NBK / 2) * 8];         // per pair: p, p' = r - q s, 1/p, s = q/p, 1/p'  (stride 8)
     double ldiag[DB];                // L_rr
     double rsbuf[DWARPS][NBK];       // per-warp 1 / sqrt(pivot) of the current panel's columns
     int flag;                        // number of panel columns published so far (monotone over the four panels)
@@ -101,11 +101,25 @@ __device__ __forceinline__ void stv(double* p, double v) {
     asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v) : "memory");
 }
 
-// Leader warp of a panel: symmetric elimination  A = Lh D Lh^T  of the 32 x 32 diagonal block at offset o, lane = row:
-//   step c:  a_ij -= (a_ic / p_c) a_jc   (i >= j > c).
-// The entry that becomes the next pivot is updated as a - (a_ic a_jc)(1/p_c), so only the hand-over, the reciprocal and
-// one DFMA separate two pivots; the whole routine is one basic block, which lets ptxas fill the chain's stall slots with
-// the trailing updates.
+// ---- one 32-column panel, eliminated two columns at a time (2 x 2 pivot blocks) -------------------------------------
+// Symmetric block elimination of columns (c, c+1) with D = [[p, q], [q, r]] (p = a_cc, q = a_{c+1,c}, r = a_{c+1,c+1}):
+//     a_ij -= [a_ic  a_i,c+1] D^-1 [a_jc  a_j,c+1]^T        (j > c+1)
+// which is exactly two consecutive scalar steps of the symmetric elimination (the second pivot is p' = r - q^2/p =
+// det(D) / p).  One pair step costs ONE reciprocal on the dependency chain (1 / det; 1 / p runs beside it) instead of two
+// dependent ones, and one shared-memory hand-over instead of two: 16 links per panel instead of 32.
+//   multipliers of row i:   m = a_ic / p,   b' = a_i,c+1 - a_ic s  (s = q / p: the updated column c+1),   m' = b' / p',
+//                           u = m - m' s,   v = m'         so that     a_ij -= u a_jc + v a_j,c+1
+//   L:   l_ic = a_ic / sqrt(p),   l_i,c+1 = b' / sqrt(p').
+// The entries of the NEXT pair's columns are updated in the form  a_ij - w_ij / det  with
+//     w_ij = (a_ic r - a_i,c+1 q) a_jc + (a_i,c+1 p - a_ic q) a_j,c+1
+// so that everything but the final DFMA is computed while the reciprocal of det is in flight.
+// pairbuf[pair][row] = (a_row,c , a_row,c+1) unscaled;  pbuf[pair] = (p, p', 1/p, s, 1/p').
+constexpr int NPAIR = NBK / 2, PB_STRIDE = 8;
+
+// Leader warp (lane = row of the diagonal block, its 32 panel entries in registers).  The whole routine is one basic
+// block, so ptxas can fill the chain's stall slots with the trailing updates.  (Measured alternatives: a leader that
+// carries only the chain, with a helper warp owning the later columns of the same rows and handing each pair back through
+// shared memory, was 2x SLOWER — the two flag hand-overs per pair cost more than the trailing updates they remove.)
 __device__ __noinline__ void panel32_lead(Smem& sm, int o, int seq0, int* status) {
     double* S = sm.S;
     const int lane = threadIdx.x & 31;
@@ -114,34 +128,44 @@ __device__ __noinline__ void panel32_lead(Smem& sm, int o, int seq0, int* status
     for (int j = 0; j < NBK; ++j) r[j] = (j <= lane) ? at(S, o + lane, o + j) : 0.0;
     bool bad = false;
 #pragma unroll
-    for (int c = 0; c < NBK; ++c) {
-        const double colc = r[c];
-        double* col = sm.colbuf + c * NBK;
-        col[lane] = colc;
+    for (int pr = 0; pr < NPAIR; ++pr) {
+        const int c = 2 * pr;
+        const double a = r[c], b = r[c + 1];
+        double2* buf = sm.pairbuf + pr * NBK;
+        buf[lane] = make_double2(a, b);
         __syncwarp();
-        const double pc = col[c];
-        const double pinv = fast_rcp(pc);
-        if (c + 1 < NBK) r[c + 1] = fma(-(colc * col[c + 1]), pinv, r[c + 1]);
-        if (lane == 0) {
-            stv(&sm.pbuf[2 * c], pc); stv(&sm.pbuf[2 * c + 1], pinv);
-            flag_store(&sm.flag, seq0 + c + 1);
+        const double2 d0 = buf[c], d1 = buf[c + 1];
+        const double p = d0.x, q = d1.x, rr = d1.y;
+        const double det = fma(p, rr, -(q * q));
+        const double dinv = fast_rcp(det);
+        const double pinv = fast_rcp(p);
+        const double e0 = fma(a, rr, -(b * q)), e1 = fma(b, p, -(a * q));     // (u, v) = (e0, e1) / det
+        if (c + 2 < NBK) {   // the next pair's two columns first: they carry the chain
+            const double2 n0 = buf[c + 2], n1 = buf[c + 3];
+            r[c + 2] = fma(-fma(e1, n0.y, e0 * n0.x), dinv, r[c + 2]);
+            r[c + 3] = fma(-fma(e1, n1.y, e0 * n1.x), dinv, r[c + 3]);
         }
-        bad |= !(pc > 0.0);
-        const double m = colc * pinv;
+        const double s = q * pinv, p2 = fma(-q, s, rr), pinv2 = p * dinv;
+        if (lane == 0) {
+            double* pb = sm.pbuf + pr * PB_STRIDE;
+            stv(pb, p); stv(pb + 1, p2); stv(pb + 2, pinv); stv(pb + 3, s); stv(pb + 4, pinv2);
+            flag_store(&sm.flag, seq0 + c + 2);
+        }
+        bad |= !(p > 0.0) | !(det > 0.0);
+        const double u = e0 * dinv, v = e1 * dinv;
 #pragma unroll
-        for (int jj = (c + 2) & ~1; jj < NBK; jj += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(col + jj);
-            if (jj >= c + 2) r[jj] = fma(-m, v.x, r[jj]);
-            r[jj + 1] = fma(-m, v.y, r[jj + 1]);
+        for (int j = c + 4; j < NBK; ++j) {
+            const double2 aj = buf[j];
+            r[j] = fma(-v, aj.y, fma(-u, aj.x, r[j]));
         }
     }
     if (bad && lane == 0) atomicExch(status, 1);   // not positive definite (or NaN): chol(): decomposition failed
 }
 
-// Follower warp: the same column steps for 32 rows below the diagonal block, four published columns at a time (one poll
-// and one batch of loads per four columns keeps a follower well ahead of the leader's pace; the panel ends one short
-// batch after the leader).  Its rows of L are scaled by 1/sqrt(pivot) and written once at the end.
-constexpr int FOLLOW_BATCH = 4;
+// Follower warp: the same pair steps for 32 rows below the diagonal block, two published pairs at a time (one poll and
+// one batch of loads per four columns keeps a follower ahead of the leader's pace; the panel ends one short batch after
+// the leader).  Its rows of L are scaled by 1/sqrt(pivot) and written once at the end.
+constexpr int FOLLOW_PAIRS = 2;
 __device__ __noinline__ void panel32_follow(Smem& sm, int o, int row, int seq0, int warp) {
     double* S = sm.S;
     const int lane = threadIdx.x & 31;
@@ -150,48 +174,61 @@ __device__ __noinline__ void panel32_follow(Smem& sm, int o, int row, int seq0, 
     for (int j = 0; j < NBK; ++j) r[j] = at(S, row, o + j);
     int have = 0;
 #pragma unroll
-    for (int cb = 0; cb < NBK; cb += FOLLOW_BATCH) {
-        if (have < seq0 + cb + FOLLOW_BATCH) have = flag_wait(&sm.flag, seq0 + cb + FOLLOW_BATCH, 100);
+    for (int pb0 = 0; pb0 < NPAIR; pb0 += FOLLOW_PAIRS) {
+        if (have < seq0 + 2 * (pb0 + FOLLOW_PAIRS)) have = flag_wait(&sm.flag, seq0 + 2 * (pb0 + FOLLOW_PAIRS), 100);
 #pragma unroll
-        for (int c = cb; c < cb + FOLLOW_BATCH; ++c) {
-            const double* col = sm.colbuf + c * NBK;
-            const double m = r[c] * ldv(&sm.pbuf[2 * c + 1]);
+        for (int pr = pb0; pr < pb0 + FOLLOW_PAIRS; ++pr) {
+            const int c = 2 * pr;
+            const double* pb = sm.pbuf + pr * PB_STRIDE;
+            const double2 ps = ldv2(pb + 2);                     // (1/p, s)
+            const double pinv2 = ldv(pb + 4);
+            const double a = r[c];
+            const double bp = fma(-a, ps.y, r[c + 1]);           // b' = a_i,c+1 - a_ic s
+            r[c + 1] = bp;                                       // kept for the final scaling
+            const double v = bp * pinv2, u = fma(-v, ps.y, a * ps.x);
+            const double* buf = reinterpret_cast<const double*>(sm.pairbuf + pr * NBK);
 #pragma unroll
-            for (int jj = (c + 1) & ~1; jj < NBK; jj += 2) {
-                const double2 v = ldv2(col + jj);
-                if (jj >= c + 1) r[jj] = fma(-m, v.x, r[jj]);
-                r[jj + 1] = fma(-m, v.y, r[jj + 1]);
+            for (int j = c + 2; j < NBK; ++j) {
+                const double2 aj = ldv2(buf + 2 * j);
+                r[j] = fma(-v, aj.y, fma(-u, aj.x, r[j]));
             }
         }
     }
-    double* rs = sm.rsbuf[warp];
-    rs[lane] = fast_rsqrt(ldv(&sm.pbuf[2 * lane]));
+    double* rs = sm.rsbuf[warp];                                 // lane c: 1 / sqrt(pivot of column c)
+    rs[lane] = fast_rsqrt(ldv(sm.pbuf + (lane >> 1) * PB_STRIDE + (lane & 1)));
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < NBK; ++c) at(S, row, o + c) = r[c] * rs[c];
 }
 
-// Scaler warp: once the leader has published all 32 columns, L entries of the diagonal block itself,
-// l_ic = a_ic / sqrt(p_c), its diagonal slot (1 / L_cc) and L_cc.
+// Scaler warp: once the leader has published all 16 pairs, L entries of the diagonal block itself
+// (l_ic = a_ic / sqrt(p), l_i,c+1 = (a_i,c+1 - a_ic s) / sqrt(p')), its diagonal slots (1 / L_cc) and L_cc.
 __device__ __forceinline__ void panel32_scale(Smem& sm, int o, int seq0, int warp) {
     double* S = sm.S;
     const int lane = threadIdx.x & 31;
     flag_wait(&sm.flag, seq0 + NBK, 300);
     double* rs = sm.rsbuf[warp];
-    const double p_mine = ldv(&sm.pbuf[2 * lane]);
+    const double p_mine = ldv(sm.pbuf + (lane >> 1) * PB_STRIDE + (lane & 1));
     const double rs_mine = fast_rsqrt(p_mine);
     rs[lane] = rs_mine;
     at(S, o + lane, o + lane) = rs_mine;
     sm.ldiag[o + lane] = p_mine * rs_mine;
     __syncwarp();
 #pragma unroll 1
-    for (int c0 = 0; c0 < NBK; c0 += 8) {   // eight volatile loads in flight, then their stores (a volatile access orders every memory operation around it)
-        double v[8];
+    for (int p0 = 0; p0 < NPAIR; p0 += 4) {   // four pairs of volatile loads in flight, then their stores
+        double2 ab[4];
+        double sv[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ldv(&sm.colbuf[(c0 + u) * NBK + lane]);
+        for (int w = 0; w < 4; ++w) {
+            ab[w] = ldv2(reinterpret_cast<const double*>(sm.pairbuf + (p0 + w) * NBK + lane));
+            sv[w] = ldv(sm.pbuf + (p0 + w) * PB_STRIDE + 3);
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (lane > c0 + u) at(S, o + lane, o + c0 + u) = v[u] * rs[c0 + u];
+        for (int w = 0; w < 4; ++w) {
+            const int c = 2 * (p0 + w);
+            if (lane > c) at(S, o + lane, o + c) = ab[w].x * rs[c];
+            if (lane > c + 1) at(S, o + lane, o + c + 1) = fma(-ab[w].x, sv[w], ab[w].y) * rs[c + 1];
+        }
     }
 }
 
@@ -389,7 +426,10 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A,
         if (warp == 0) panel32_lead(sm, o, o, status);
         else if (warp < NPAN - b) panel32_follow(sm, o, o + NBK * warp + lane, o, warp);
         else if (warp == SCALER_WARP) panel32_scale(sm, o, o, warp);
-        else if (b > 0 && warp >= NPAN) store_L_columns(sm, A, lda, nb, o - NBK, warp - NPAN, SCALER_WARP - NPAN);
+        else if (b > 0 && warp == 6) {                                       // under panels 1..3: the previous panel's leftovers
+            inv32(sm, o - NBK, lane);                                        //   inverse of its diagonal block
+            store_L_columns(sm, A, lda, nb, o - NBK, 0, 1);                  //   its columns of L to global memory
+        }
         stamp();
         __syncthreads();
         stamp();
@@ -399,12 +439,12 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_diag128(double* __restrict__ A,
         }
         stamp();
     }
-    // ---- inverse: diagonal 32-blocks (warps 0-3; warps 4-7 write the last panel's columns of L meanwhile), then the
+    // ---- inverse: the last diagonal 32-block (warp 0; the others write the last panel's columns of L meanwhile), then the
     // off-diagonal blocks of the 64- and 128-level; every piece of X goes to global memory as soon as it is final, so the
     // stores drain under the remaining products and only the last 64 x 64 block is left when the kernel ends (the strict
     // upper triangle of Dinv is never written: the caller zero-initialises it once) ----
-    if (warp < NPAN) inv32(sm, warp * NBK, lane);
-    else store_L_columns(sm, A, lda, nb, DB - NBK, warp - NPAN, DWARPS - NPAN);
+    if (warp == 0) inv32(sm, DB - NBK, lane);                              // blocks 0..2 were inverted under the later panels
+    else store_L_columns(sm, A, lda, nb, DB - NBK, warp - 1, DWARPS - 1);
     __syncthreads();
     stamp();
     store_X_diag_blocks(sm, Dinv, ldd, nb, warp, lane);
