@@ -408,12 +408,19 @@ def main():
         # the int8 ceiling is MEASURED in this run: tcgen05.mma.kind::i8 (M128 N256 K32, operands in shared memory) issued
         # back to back on every SM (gpirt_b200_int8_peak_tops); MEASURED_PEAKS.json has no int8 figure
         i8_peak = G.int8_peak_tops()
+        i8_peak_rand = G.int8_peak_tops(random_operands=True)
         alg = 36.0 * fp64_work
         peak = iso_peak = i8_peak
         achieved, iso, unit = alg / dom_ms * 1e-9, alg / iso_ms * 1e-9, "TOP/s"
         peak_src = ("tcgen05.mma.kind::i8 issue-rate microbenchmark measured in this run (%.0f TOP/s; nominal dense int8 4500; "
                     "2 x the dense bf16 figure of MEASURED_PEAKS.json would be %.0f)" % (i8_peak, 2.0 * peaks["bf16_tflops"]))
         i8_note = {"plane_pair_products": 36, "fp64_tensor_peak_tflops": dmma,
+                   "power_limited_peak": {"value": i8_peak_rand, "unit": "TOP/s",
+                                          "frac": alg / dom_ms * 1e-9 / i8_peak_rand, "frac_isolated": alg / iso_ms * 1e-9 / i8_peak_rand,
+                                          "note": "the same issue-rate microbenchmark with pseudo-random digit planes as operands: "
+                                                  "identical cycles per MMA, but the switching power pulls the SM clock down "
+                                                  "(profiles/r02_umma_i8_shapes.txt); `peak` / `frac` above stay on the "
+                                                  "near-constant-operand figure, the stricter denominator"},
                    "fp64_equivalent_tflops": fp64_work / dom_ms * 1e-9, "fp64_equivalent_tflops_isolated": fp64_work / iso_ms * 1e-9,
                    "segments_ms": {k: seg_ms[k] for k in segs}, "segments_ms_isolated": {k: t_iso[k][0] / Ki for k in segs},
                    "note": "`achieved` counts the 36 exact int8 plane-pair products the scheme EXECUTES per FP64 product; the "

@@ -18,7 +18,7 @@ EXPORTS = [
     "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_set_pipeline",
     "gpirt_b200_sampler_launches", "gpirt_b200_sampler_uses",
     "gpirt_b200_sampler_destroy", "gpirt_b200_se_cov", "gpirt_b200_chol_lower", "gpirt_b200_dgemm", "gpirt_b200_dgemm_i8",
-    "gpirt_b200_trsm_lower", "gpirt_b200_ll_bar", "gpirt_b200_fp64_peak_tflops", "gpirt_b200_int8_peak_tops", "gpirt_b200_rng_probe", "gpirt_b200_response_matrix", "gpirt_b200_theta_diagnostics",
+    "gpirt_b200_trsm_lower", "gpirt_b200_ll_bar", "gpirt_b200_fp64_peak_tflops", "gpirt_b200_int8_peak_tops", "gpirt_b200_int8_peak_tops_random", "gpirt_b200_rng_probe", "gpirt_b200_response_matrix", "gpirt_b200_theta_diagnostics",
 ]
 
 # enums of include/gpirt_b200.h
@@ -89,6 +89,7 @@ def load():
     L.gpirt_b200_ll_bar.argtypes = [_dp, _dp, _dp, C.c_int64, C.c_int64, _dp]
     L.gpirt_b200_fp64_peak_tflops.argtypes = [_dp, _dp]
     L.gpirt_b200_int8_peak_tops.argtypes = [_dp]
+    L.gpirt_b200_int8_peak_tops_random.argtypes = [_dp]
     _ip64 = C.POINTER(C.c_int64)
     L.gpirt_b200_response_matrix.argtypes = [_dp, C.c_int64, C.c_int64, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _ip64, _ip64, _ip64]
     L.gpirt_b200_theta_diagnostics.argtypes = [_dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp]

@@ -324,6 +324,10 @@ int gpirt_b200_int8_peak_tops(double* tops) {
     GP_TRY(have_device());
     return int8_peak_tops(tops);
 }
+int gpirt_b200_int8_peak_tops_random(double* tops) {
+    GP_TRY(have_device());
+    return int8_peak_tops(tops, 1);
+}
 
 int gpirt_b200_rng_probe(uint64_t seed, uint32_t sweep, uint32_t purpose, uint32_t stream, uint32_t idx0, int count,
                          double* uniforms, double* normals) {

@@ -8,6 +8,10 @@
 #include <atomic>
 #include <cstring>
 #include <ctime>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -1087,6 +1091,90 @@ void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s) {
 // ----------------------------------------------------------------------------------------------------------------------
 // gpirtMCMC(): src/gpirtMCMC.cpp:5-117
 // ----------------------------------------------------------------------------------------------------------------------
+// Draw storage runs on its own host thread: the caller's arrays are fresh pageable memory, and a slice of f draws
+// (n m doubles) takes 2-3 sweeps' worth of time to land there.  The sampling thread only snapshots the state on the device
+// (two buffers) and hands the slot to this worker, which waits for the snapshot, moves it over PCIe and into the caller's
+// arrays while the sampling thread keeps the GPU's launch queue full.  With thinned draws the stores disappear behind
+// the sweeps; with every draw stored the worker is the bottleneck and the sampling thread waits for a free buffer.
+namespace {
+struct StoreWorker {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> jobs;              // slots to drain, in order
+    int drained[2] = {-1, -1};         // last slot drained from snapshot buffer b (a buffer is free when nothing is queued on it)
+    int queued[2] = {-1, -1};          // last slot queued on buffer b
+    bool quit = false;
+    int rc = GPIRT_B200_OK;            // first failure of a drain
+    std::string error;
+    std::function<int(int)> drain;     // runs on the worker thread
+    std::thread th;
+    int device = 0;
+    double busy_s = 0.0;
+
+    void start() {
+        th = std::thread([this] {
+            cudaSetDevice(device);
+            for (;;) {
+                int slot;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [this] { return quit || !jobs.empty(); });
+                    if (jobs.empty()) return;          // quit with nothing left
+                    slot = jobs.front();
+                    jobs.pop_front();
+                }
+                int r = GPIRT_B200_OK;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    r = rc;
+                }
+                if (r == GPIRT_B200_OK) {              // after a failure the remaining jobs are dropped
+                    r = drain(slot);
+                    if (r != GPIRT_B200_OK) {
+                        std::lock_guard<std::mutex> lk(mu);
+                        rc = r;
+                        error = last_error();
+                    }
+                }
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    drained[slot & 1] = slot;
+                }
+                cv.notify_all();
+            }
+        });
+    }
+    void push(int slot) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobs.push_back(slot);
+            queued[slot & 1] = slot;
+        }
+        cv.notify_all();
+    }
+    void wait_buffer_free(int b) {       // the previous slot snapshotted into buffer b has reached the host
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return drained[b] == queued[b]; });
+    }
+    void wait_idle() { wait_buffer_free(0); wait_buffer_free(1); }
+    int status(std::string* msg) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc != GPIRT_B200_OK && msg) *msg = error;
+        return rc;
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            jobs.clear();
+        }
+        cv.notify_all();
+        th.join();
+    }
+};
+}  // namespace
+
 static thread_local int64_t g_last_degenerate_theta = 0;
 int64_t gpirt_b200_last_degenerate_theta(void) { return g_last_degenerate_theta; }
 
@@ -1134,15 +1222,16 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     // enqueues sweep t+1, and only then blocks in the device-to-host copy of snapshot t on a second stream.
     struct Guard {
         gpirt_b200_sampler* s; cudaStream_t copy; cudaEvent_t ev[2]; double* snap_f[2]; double* snap_small[2];
-        double *f_mean, *f_m2, *agree_dev; int* h_poll;
+        double *f_mean, *f_m2, *agree_dev; int* h_poll; StoreWorker* worker;
         ~Guard() {
+            if (worker) { worker->stop(); delete worker; }   // before anything it uses goes away
             if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
             for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); pool_free(snap_f[i], s->stream); pool_free(snap_small[i], s->stream); }
             pool_free(f_mean, s->stream); pool_free(f_m2, s->stream); pool_free(agree_dev, s->stream);
             if (h_poll) cudaFreeHost(h_poll);
             gpirt_b200_sampler_destroy(s);
         }
-    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr};
+    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int n_slots = sample_iterations / thin + 1;         // slot 0 = initial values, slot k = sampling iteration k * thin
     const size_t nm = (size_t)n * m;
     if (keep_f && !getenv("GPIRT_NO_HUGEPAGE_HINT")) {
@@ -1154,10 +1243,11 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     }
     std::vector<double> small((size_t)n + 2 * (size_t)m);
     GP_CUDA(cudaStreamCreateWithFlags(&gd.copy, cudaStreamNonBlocking));
-    GP_CUDA(cudaHostAlloc((void**)&gd.h_poll, 4 * sizeof(int) + 8 * sizeof(double), cudaHostAllocDefault));
-    std::memset(gd.h_poll, 0, 4 * sizeof(int) + 8 * sizeof(double));   // [0..3] status words, then a ring of 8 agreed stop flags
-    double* h_ring = reinterpret_cast<double*>(gd.h_poll + 4);
-    int agree_count = 0, agree_at_snapshot[2] = {-1, -1};
+    GP_CUDA(cudaHostAlloc((void**)&gd.h_poll, 8 * sizeof(int) + 8 * sizeof(double), cudaHostAllocDefault));
+    std::memset(gd.h_poll, 0, 8 * sizeof(int) + 8 * sizeof(double));   // [0..3] status words polled by this thread, [4..7] by the
+    double* h_ring = reinterpret_cast<double*>(gd.h_poll + 8);         // storage worker, then a ring of 8 agreed stop flags
+    volatile int* w_poll = gd.h_poll + 4;
+    int agree_count = 0;
     for (int i = 0; i < 2; ++i) {
         GP_CUDA(cudaEventCreateWithFlags(&gd.ev[i], cudaEventDisableTiming));
         GP_TRY(pool_alloc((void**)&gd.snap_small[i], small.size() * sizeof(double), s->stream));
@@ -1171,7 +1261,7 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     if (sharded) GP_TRY(pool_alloc((void**)&gd.agree_dev, sizeof(double), s->stream));
     double t_c = now();
     GP_TRY(s->init_draws());
-    double t_d = now(), t_store = 0.0;
+    double t_d = now();
     // snapshot(slot): main stream copies theta | beta (and f, tightly packed) into buffer slot & 1 and records the event
     auto snapshot = [&](int slot) -> int {
         const int b = slot & 1;
@@ -1181,41 +1271,51 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
             GP_CUDA(cudaMemcpy2DAsync(gd.snap_f[b], (size_t)n * sizeof(double), s->f, s->ldn * sizeof(double), (size_t)n * sizeof(double),
                                       (size_t)m, cudaMemcpyDeviceToDevice, s->stream));
         GP_CUDA(cudaEventRecord(gd.ev[b], s->stream));
-        agree_at_snapshot[b] = agree_count - 1;   // the newest agreement this snapshot's event covers
         return GPIRT_B200_OK;
     };
-    // drain(slot): copy stream waits for the snapshot, then the host blocks in the device-to-host copies.  The sampler's
-    // status words (Cholesky / ESS failure) ride along, so a failed chain stops at the next stored slot instead of
-    // spinning every item through the ESS iteration cap for the rest of the run.
-    auto drain = [&](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
+    // drain(slot), on the storage worker: the copy stream waits for the snapshot, then the worker blocks in the
+    // device-to-host copies.  The sampler's status words (Cholesky / ESS failure) ride along, so a failed chain is noticed
+    // at the next stored slot instead of spinning every item through the ESS iteration cap for the rest of the run.
+    gd.worker = new StoreWorker();
+    StoreWorker& worker = *gd.worker;
+    GP_CUDA(cudaGetDevice(&worker.device));
+    worker.drain = [&, n_slots](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
         const double ts0 = now();
         const int b = slot & 1;
         GP_CUDA(cudaStreamWaitEvent(gd.copy, gd.ev[b], 0));
-        GP_CUDA(cudaMemcpyAsync(gd.h_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, gd.copy));
+        GP_CUDA(cudaMemcpyAsync((void*)w_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, gd.copy));
         GP_CUDA(cudaMemcpyAsync(small.data(), gd.snap_small[b], small.size() * sizeof(double), cudaMemcpyDeviceToHost, gd.copy));
         if (keep_f) GP_TRY(chunked_d2h(f_out + (size_t)slot * nm, gd.snap_f[b], nm, b, gd.copy));
         GP_CUDA(cudaStreamSynchronize(gd.copy));
         for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * n_slots + slot] = small[i];
         std::memcpy(beta_out + (size_t)slot * 2 * m, small.data() + n, 2 * (size_t)m * sizeof(double));
-        t_store += now() - ts0;
+        worker.busy_s += now() - ts0;
         return GPIRT_B200_OK;
     };
-    // Stopping early (interrupt from the progress callback, failed Cholesky / ESS seen in the polled status words) must be
-    // a COMMON decision when items are sharded: a rank that returned alone would leave its peers blocked in the next
-    // sweep's collectives.  Every rank therefore enqueues, at the same points of the iteration sequence, a one-word
-    // all-reduce of its local stop request on the sampler's stream and acts on the agreed value of a GIVEN agreement (ring
-    // slot) at the host sync that covers it — the same program point on every rank.
+    worker.start();
+    struct WorkerStop {   // declared after everything the drain closure refers to: the worker is joined before any of it dies
+        StoreWorker* w;
+        ~WorkerStop() { w->stop(); }
+    } worker_stop{gd.worker};
+    // Stopping early (interrupt from the progress callback, failed Cholesky / ESS seen in the polled status words, a failed
+    // store) must be a COMMON decision when items are sharded: a rank that returned alone would leave its peers blocked in
+    // the next sweep's collectives.  Every rank therefore enqueues, every 8th iteration, a one-word all-reduce of its local
+    // stop request on the sampler's stream and acts on the agreed value after the host sync that follows it — the same
+    // program point on every rank.  An unsharded chain stops as soon as it sees a reason.
     bool want_stop = false;
     int stop_code = GPIRT_B200_OK;
     auto local_stop_code = [&]() -> int {
-        if (gd.h_poll[0]) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
-        if (gd.h_poll[1]) { set_last_error("elliptical slice sampler did not terminate (NaN log-likelihood?)"); return GPIRT_B200_ERR_ESS; }
+        std::string msg;
+        const int wrc = worker.status(&msg);
+        if (wrc != GPIRT_B200_OK) { set_last_error("%s", msg.c_str()); return wrc; }
+        if (gd.h_poll[0] || w_poll[0]) { set_last_error("chol(): decomposition failed"); return GPIRT_B200_ERR_NOT_PD; }
+        if (gd.h_poll[1] || w_poll[1]) { set_last_error("elliptical slice sampler did not terminate (NaN log-likelihood?)"); return GPIRT_B200_ERR_ESS; }
         if (want_stop) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
         return GPIRT_B200_OK;
     };
     auto enqueue_agreement = [&]() -> int {
         if (!sharded) return GPIRT_B200_OK;
-        const double mine = (want_stop || gd.h_poll[0] || gd.h_poll[1]) ? 1.0 : 0.0;   // pageable source: staged at call time
+        const double mine = local_stop_code() != GPIRT_B200_OK ? 1.0 : 0.0;   // pageable source: staged at call time
         GP_CUDA(cudaMemcpyAsync(gd.agree_dev, &mine, sizeof(double), cudaMemcpyHostToDevice, s->stream));
         GP_TRY(comm_allreduce_sum_f64(s->comm, gd.agree_dev, 1, s->stream));
         GP_CUDA(cudaMemcpyAsync(h_ring + (agree_count & 7), gd.agree_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1232,14 +1332,14 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
         return stop_code != GPIRT_B200_OK;
     };
     GP_TRY(snapshot(0));                                                            // :53-55 initial values
-    int pending = 0;                                                                // slot whose snapshot is not drained yet
+    worker.push(0);
     const int total = sample_iterations + burn_iterations;
     const double inc = total > 0 ? 100.0 / total : 0.0;
     double progress = 0.0;
     int n_summarised = 0;
     for (int iter = 0; iter < total; ++iter) {
         if (cb && cb(progress, cb_ctx)) want_stop = true;                           // Rcpp::checkUserInterrupt, :66,85
-        if (want_stop && !sharded) { set_last_error("interrupted by the progress callback"); return GPIRT_B200_ERR_INTERRUPT; }
+        if (!sharded && stop_now(-1)) return stop_code;                             // interrupt, failed store, failed chain seen by the worker
         progress += inc;
         const bool sampling = iter >= burn_iterations;
         const int si = iter - burn_iterations + 1;                                  // 1-based sampling iteration
@@ -1249,27 +1349,29 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
             dim3 grid((unsigned)m, (unsigned)ceil_div(n, 256));
             GP_LAUNCH(k_f_welford, grid, 256, 0, s->stream, s->f, s->ldn, (int)n, (double)(++n_summarised), gd.f_mean, gd.f_m2);
         }
-        const bool sync_point = store || (iter & 7) == 7;
-        if (sync_point) GP_TRY(enqueue_agreement());
-        if (pending >= 0) {                                                         // previous slot goes out while the sweep runs
-            const int covered = agree_at_snapshot[pending & 1];
-            GP_TRY(drain(pending));
-            pending = -1;
-            if (stop_now(covered)) return stop_code;
-        } else if ((iter & 7) == 7) {                                               // keep progress / interrupts honest between stores
+        if (store) {
+            const int slot = si / thin;                                             // :99-103
+            worker.wait_buffer_free(slot & 1);                                      // slot - 2 has left this snapshot buffer
+            GP_TRY(snapshot(slot));
+            worker.push(slot);
+        }
+        if ((iter & 7) == 7) {                                                      // bounded run-ahead; progress / interrupts stay honest
+            GP_TRY(enqueue_agreement());
             GP_CUDA(cudaMemcpyAsync(gd.h_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
             GP_CUDA(cudaStreamSynchronize(s->stream));
             if (stop_now(agree_count - 1)) return stop_code;
         }
-        if (store) {
-            const int slot = si / thin;                                             // :99-103
-            GP_TRY(snapshot(slot));
-            pending = slot;
-        }
     }
-    if (pending >= 0) GP_TRY(drain(pending));
+    worker.wait_idle();
+    const double t_store = worker.busy_s;
+    {
+        std::string msg;
+        const int wrc = worker.status(&msg);
+        if (wrc != GPIRT_B200_OK) { set_last_error("%s", msg.c_str()); return wrc; }
+    }
+    GP_CUDA(cudaMemcpyAsync(gd.h_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     GP_CUDA(cudaStreamSynchronize(s->stream));
-    if (stop_now(agree_count - 1)) return stop_code;
+    if (!sharded && stop_now(-1)) return stop_code;
     GP_TRY(s->check_status());
     {
         int h[4] = {0, 0, 0, 0};

@@ -176,14 +176,22 @@ k_igemm_theta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // One CTA per SM; one elected thread issues `iters` x 4 tcgen05.mma.kind::i8 (M128 N256 K32, both operands from shared
 // memory in the SWIZZLE_128B layout of the real kernels) back to back into two alternating TMEM accumulators, with no
 // loads at all: what the tensor pipe sustains when nothing else limits it.  2 x 128 x 256 x 32 int8 operations per MMA.
-__global__ void __launch_bounds__(128, 1) k_peak_umma_i8(int iters, unsigned* sink) {
+__global__ void __launch_bounds__(128, 1) k_peak_umma_i8(int iters, unsigned* sink, int random_operands) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + TI_STAGE_BYTES);
     const uint32_t done = smem_u32(bars);
     uint32_t* tmem_slot = (uint32_t*)(bars + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < TI_STAGE_BYTES / 4; i += 128) ((uint32_t*)smem)[i] = 0x01010101u * (uint32_t)(i & 3);
+    for (int i = tid; i < TI_STAGE_BYTES / 4; i += 128) {
+        uint32_t w = 0x01010101u * (uint32_t)(i & 3);   // near-constant operands: the pipe's issue rate at low switching power
+        if (random_operands) {                          // digits spread over [-64, 63] like real operand planes
+            uint32_t x = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+            x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+            w = (x & 0x3f3f3f3fu) | (((x >> 6) & 0x01010101u) * 0xc0u);
+        }
+        ((uint32_t*)smem)[i] = w;
+    }
     if (tid == 0) {
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -386,11 +394,11 @@ void ThetaInt8::destroy() {
     ready = false;
 }
 
-int int8_peak_tops(double* tops) {
+int int8_peak_tops(double* tops, int random_operands) {
     int dev = 0, sms = 0;
     GP_CUDA(cudaGetDevice(&dev));
     GP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int smem = TI_STAGE_BYTES + 1024 + 256, iters = 20000;
+    const int smem = TI_STAGE_BYTES + 1024 + 256, iters = random_operands ? 60000 : 20000;   // long enough for the clocks to settle
     GP_CUDA(cudaFuncSetAttribute(k_peak_umma_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned* sink = nullptr;
     GP_CUDA(cudaMalloc((void**)&sink, (size_t)sms * sizeof(unsigned)));
@@ -400,7 +408,7 @@ int int8_peak_tops(double* tops) {
     cudaError_t err = cudaSuccess;
     for (int r = 0; r < 4 && err == cudaSuccess; ++r) {
         cudaEventRecord(e0);
-        GP_LAUNCH(k_peak_umma_i8, (unsigned)sms, 128, smem, 0, iters, sink);
+        GP_LAUNCH(k_peak_umma_i8, (unsigned)sms, 128, smem, 0, iters, sink, random_operands);
         cudaEventRecord(e1);
         err = cudaEventSynchronize(e1);
         float t = 0.f;

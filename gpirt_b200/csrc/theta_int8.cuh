@@ -26,6 +26,6 @@ struct ThetaInt8 {
 
 // sustained rate of tcgen05.mma.kind::i8 (M128 N256 K32, operands in shared memory) on every SM at once, in 10^12 int8
 // operations per second: the measured tensor-pipe ceiling the int8 kernels are judged against
-int int8_peak_tops(double* tops);
+int int8_peak_tops(double* tops, int random_operands = 0);
 
 }  // namespace gpirt

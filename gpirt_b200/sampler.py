@@ -269,10 +269,12 @@ def theta_diagnostics(theta_chains):
     return rhat, ess
 
 
-def int8_peak_tops():
-    """measured tcgen05.mma.kind::i8 issue-rate peak of the device, 10^12 int8 operations per second"""
+def int8_peak_tops(random_operands=False):
+    """measured tcgen05.mma.kind::i8 issue-rate peak of the device, 10^12 int8 operations per second (random_operands:
+    with pseudo-random digit planes instead of near-constant ones — lower, the SM clock drops under the switching power)"""
     a = C.c_double(0)
-    _lib.check(_lib.load().gpirt_b200_int8_peak_tops(C.byref(a)))
+    L = _lib.load()
+    _lib.check((L.gpirt_b200_int8_peak_tops_random if random_operands else L.gpirt_b200_int8_peak_tops)(C.byref(a)))
     return a.value
 
 

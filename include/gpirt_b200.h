@@ -172,6 +172,10 @@ int gpirt_b200_fp64_peak_tflops(double* dmma_tflops, double* dfma_tflops);
 /* int8 tensor-pipe peak of the current device in 10^12 operations/s: tcgen05.mma.kind::i8 (M128 N256 K32, operands in
  * shared memory) issued back to back on every SM with no loads (roofline denominator of the int8 kernels) */
 int gpirt_b200_int8_peak_tops(double* tops);
+/* the same microbenchmark with pseudo-random digits in [-64, 63] as operands: the MMAs issue at the same rate in cycles
+ * (tools/umma_i8_shapes.cu), but the switching power pulls the SM clock down, so the sustained operations/s are lower —
+ * the practical ceiling of a kernel that multiplies real operand planes */
+int gpirt_b200_int8_peak_tops_random(double* tops);
 /* ---- the host steps either side of the sampler ---- */
 /* Response coding, the producer of y (reference R/response_matrix.R:79-98) for numeric code matrices, on the device:
  * codes n x m (column-major doubles, NaN = NA); yea / nay / missing code lists; cells with a code in none of the lists are
