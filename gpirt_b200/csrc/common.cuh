@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdint>
 #include <mutex>
+#include <utility>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -58,11 +59,29 @@ struct DeviceOnce {
     ~DeviceOnce() { if (slot) *slot = true; }
 };
 
-// launch counter (gpu_launches in bench.py): every kernel launch in this library goes through GP_LAUNCH
+// launch counter (gpu_launches in bench.py): every kernel launch in this library goes through GP_LAUNCH.
+// The launch carries the priority of its stream as an explicit launch attribute: a plain launch inherits it from the
+// stream anyway, but a kernel node CAPTURED into a CUDA graph keeps only what the launch itself says — without it the
+// replayed sweep runs the Cholesky chain at the same priority as the bulk products it is supposed to overtake.
 extern std::atomic<int64_t> g_launch_count;
+template <typename... KArgs, typename... Args>
+inline void launch_with_stream_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int prio = 0;
+    cfg.numAttrs = 0;
+    if (stream != nullptr && cudaStreamGetPriority(stream, &prio) == cudaSuccess) {
+        attr[0].id = cudaLaunchAttributePriority;
+        attr[0].val.priority = prio;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 #define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
     do {                                                                                           \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
+        ::gpirt::launch_with_stream_priority(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__); \
         ++::gpirt::g_launch_count;                                                                 \
     } while (0)
 

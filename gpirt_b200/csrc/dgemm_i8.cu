@@ -148,12 +148,13 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 // cluster, all on the same row tile): ntiles, group_cols and total count those groups.
 struct TileSched {
     int mtiles, ntiles, group_cols, total, ascending;   // ascending: row tile 0 is the heaviest (upper-triangular A)
+    int mtile0;                                          // first row tile with work (rows above it are skipped entirely)
     // order index -> (row tile, column tile): column tiles in groups whose planes stay in L2, row tiles heaviest first
     __device__ __forceinline__ void at(int o, int& r, int& c) const {
         const int per_group = group_cols * mtiles;
         const int g = o / per_group, o2 = o - g * per_group;
         const int gw = min(group_cols, ntiles - g * group_cols);
-        r = ascending ? o2 / gw : mtiles - 1 - o2 / gw;
+        r = mtile0 + (ascending ? o2 / gw : mtiles - 1 - o2 / gw);
         c = g * group_cols + o2 % gw;
     }
 };
@@ -524,7 +525,10 @@ int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double
     const int n_sm = sm_count[dev];
     if (B.rows_pad % (DG_BN * cn) != 0) { set_last_error("dgemm_i8: B operand is not padded to whole clusters"); return GPIRT_B200_ERR_ARG; }
     TileSched sched;
-    sched.mtiles = (int)(A.rows_pad / DG_BM);
+    // an accumulating slice of a lower-triangular product adds nothing to the rows above its first column
+    sched.mtile0 = (a_tri == DG_TRI_LOWER && accumulate) ? k_lo / DG_BM : 0;
+    sched.mtiles = (int)(A.rows_pad / DG_BM) - sched.mtile0;
+    if (sched.mtiles <= 0) return GPIRT_B200_OK;
     sched.ntiles = (int)(B.rows_pad / (DG_BN * cn));
     const int gc = group_cols > 0 ? (int)ceil_div(group_cols, cn) : 0;
     sched.group_cols = gc > 0 ? min(gc, sched.ntiles) : sched.ntiles;
@@ -540,11 +544,20 @@ int dgemm_i8(cudaStream_t st, const DigitPlanes& A, const DigitPlanes& B, double
     cfg.blockDim = dim3(DG_THREADS);
     cfg.dynamicSmemBytes = DG_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cn; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int prio = 0, na = 0;
+    if (st != nullptr && cudaStreamGetPriority(st, &prio) == cudaSuccess) {   // explicit: survives capture into a graph (common.cuh)
+        attr[na].id = cudaLaunchAttributePriority;
+        attr[na].val.priority = prio;
+        ++na;
+    }
+    if (cn > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cn; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = cn > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     const CUtensorMap& ma = cn > 1 ? A.map->m_part : A.map->m;
     const int a_rows_pad = (int)A.rows_pad, b_rows_pad = (int)B.rows_pad, kb_lo = k_lo / DG_KB, kb_hi = (int)ceil_div(k_hi, DG_KB);
     const int acc = accumulate ? 1 : 0;

@@ -13,7 +13,7 @@ static int launch_cfg(cudaStream_t stream, const GemmArgs& g) {
         DeviceOnce once(configured);
         if (once.first) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    dim3 grid((unsigned)(ceil_div(g.N, BN) * ceil_div(g.M, BM)), 1, (unsigned)g.batch);
+    dim3 grid((unsigned)(ceil_div(g.N, BN) * ceil_div(g.M, BM)), (unsigned)(g.splitk > 1 ? g.splitk : 1), (unsigned)g.batch);
     GP_LAUNCH(kern, grid, dim3(WM * WN * 32), smem, stream, g);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
@@ -37,6 +37,7 @@ static int launch_layout(cudaStream_t stream, const GemmArgs& g) {
 
 int gemm_f64(cudaStream_t stream, bool ta, bool tb, const GemmArgs& g) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return GPIRT_B200_OK;
+    if (g.splitk > 1 && (!g.ws || !g.ws_count || g.tri == TRI_C_LOWER)) { set_last_error("gemm_f64: split-K needs a workspace and a full C"); return GPIRT_B200_ERR_ARG; }
     if (ta && tb) { set_last_error("gemm_f64: op(A)=T with op(B)=T is not instantiated"); return GPIRT_B200_ERR_ARG; }
     if (ta) return launch_layout<true, false>(stream, g);
     if (tb) return launch_layout<false, true>(stream, g);

@@ -38,6 +38,13 @@ struct GemmArgs {
     int batch = 1;      // blockIdx.z indexes independent problems at fixed pointer strides
     int64_t strideA = 0, strideB = 0, strideC = 0;
     int force_big = 0;  // always use the 128 x 128 tile (needed when C aliases A or B and N <= 128: one N tile)
+    // split-K for thin products (few output tiles, long K): blockIdx.y owns a contiguous range of k-tiles and writes its
+    // partial tile to `ws`; the CTA that arrives last at the tile's counter adds the partials IN SPLIT ORDER (the result
+    // does not depend on the arrival order: deterministic) and applies alpha / beta.  ws: tiles x splitk x BM x BN doubles;
+    // ws_count: one int per tile (x batch), zero before the first use — the finishing CTA resets it.
+    int splitk = 1;
+    double* ws = nullptr;
+    int* ws_count = nullptr;
 };
 
 constexpr int GEMM_BK = 16;
@@ -104,7 +111,12 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
     if (g.tri == TRI_A_LOWER) k_end = min(g.K, m0 + BM);
     if (g.tri == TRI_A_UPPER) k_begin = (m0 / BK) * BK;
     if (g.tri == TRI_B_LOWER) k_begin = (n0 / BK) * BK;
-    const int nkt = (k_end - k_begin + BK - 1) / BK;
+    int nkt = (k_end - k_begin + BK - 1) / BK;
+    int kt0 = 0;                                  // first k-tile of this CTA's share
+    if (g.splitk > 1) {
+        const int lo = (int)((int64_t)nkt * blockIdx.y / g.splitk), hi = (int)((int64_t)nkt * (blockIdx.y + 1) / g.splitk);
+        kt0 = lo; nkt = hi - lo;
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nkt) load_part(s, s, 0, 1);
+        if (s < nkt) load_part(s, kt0 + s, 0, 1);
         cp_async_commit();
     }
     constexpr int KSTEPS = BK / 4;
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
             const int kk = ks * 4;
-            if (do_load) load_part(lstage, nxt, ks, KSTEPS);   // the next tile's loads are spread over the k-steps
+            if (do_load) load_part(lstage, kt0 + nxt, ks, KSTEPS);   // the next tile's loads are spread over the k-steps
             double a[MI], b[NI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
@@ -200,6 +212,43 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_f64_kernel(cons
         cp_async_commit();
     }
     cp_async_wait<0>();
+
+    if (g.splitk > 1) {   // partial tile -> workspace; the last CTA of the tile reduces in split order
+        __shared__ int s_last;
+        const int tile_lin = (int)(blockIdx.z * gridDim.x + blockIdx.x);
+        double* wsp = g.ws + ((int64_t)tile_lin * g.splitk + blockIdx.y) * (BM * BN) + tid;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                __stcg(wsp + ((i * NI + j) * 2 + 0) * THREADS, acc[i][j][0]);
+                __stcg(wsp + ((i * NI + j) * 2 + 1) * THREADS, acc[i][j][1]);
+            }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int prev = atomicAdd(g.ws_count + tile_lin, 1);
+            s_last = (prev == g.splitk - 1);
+            if (s_last) g.ws_count[tile_lin] = 0;   // ready for the next launch on this stream
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const double* rd = g.ws + (int64_t)tile_lin * g.splitk * (BM * BN) + tid;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int sp = 0; sp < g.splitk; ++sp, rd += BM * BN) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    acc[i][j][0] += __ldcg(rd + ((i * NI + j) * 2 + 0) * THREADS);
+                    acc[i][j][1] += __ldcg(rd + ((i * NI + j) * 2 + 1) * THREADS);
+                }
+        }
+    }
 
     // epilogue: C fragment (row = g, cols = 2t, 2t+1).  Two passes so that, with beta != 0, all loads of the old C are
     // in flight together instead of being serialised behind the stores (the compiler cannot prove they do not alias).

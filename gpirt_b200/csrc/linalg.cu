@@ -135,7 +135,7 @@ static int launch_panel_update(cudaStream_t stream, double* A, int64_t lda, int 
         if (once.first) GP_CUDA(cudaFuncSetAttribute(panel::k_panel_update<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int rem = n - k0 - CHOL_NB;
-    GP_LAUNCH(panel::k_panel_update<R>, (unsigned)ceil_div(rem, R), panel::PTHREADS, smem, stream, A, lda, n, k0, Dinv, ldd, counter);
+    GP_LAUNCH(panel::k_panel_update<R>, (unsigned)ceil_div(rem, R), panel::PTHREADS, smem, stream, A, lda, n, k0, Dinv, ldd, counter, (long long*)nullptr, 0);
     GP_CUDA(cudaGetLastError());
     return GPIRT_B200_OK;
 }
@@ -238,11 +238,32 @@ __global__ void k_scatter_block_inverses(const double* __restrict__ Dinv, int64_
     if (r / CHOL_NB == c / CHOL_NB) X[r + (int64_t)c * ldx] = Dinv[r + (int64_t)(c % CHOL_NB) * ldd];
 }
 
+// one level-s merge of `batch` pairs starting at row/column o (pair stride 2s): X21 = -X22 (L21 X11), `rows` = order of X22
+static int trtri_merge(cudaStream_t stream, const double* L, int64_t ldl, double* X, int64_t ldx, double* T, int64_t ldt, int64_t o,
+                       int64_t s, int rows, int batch, double* ws, int* ws_count) {
+    GemmArgs a;   // T21 = L21 X11   (X11 lower triangular)
+    a.M = rows; a.N = (int)s; a.K = (int)s;
+    a.A = L + (o + s) + o * ldl; a.lda = ldl; a.B = X + o + o * ldx; a.ldb = ldx;
+    a.C = T + (o + s) + o * ldt; a.ldc = ldt; a.tri = TRI_B_LOWER;
+    a.batch = batch;
+    a.strideA = 2 * s * (ldl + 1); a.strideB = 2 * s * (ldx + 1); a.strideC = 2 * s * (ldt + 1);
+    if (ws && ws_count && a.K >= 512) { a.splitk = (int)std::min<int64_t>(8, a.K / 128); a.ws = ws; a.ws_count = ws_count; }
+    GP_TRY(gemm_f64(stream, false, false, a));
+    GemmArgs b;   // X21 = -X22 T21  (X22 lower triangular)
+    b.M = rows; b.N = (int)s; b.K = rows;
+    b.A = X + (o + s) + (o + s) * ldx; b.lda = ldx; b.B = T + (o + s) + o * ldt; b.ldb = ldt;
+    b.C = X + (o + s) + o * ldx; b.ldc = ldx; b.alpha = -1.0; b.tri = TRI_A_LOWER;
+    b.batch = batch; b.strideA = 2 * s * (ldx + 1); b.strideB = 2 * s * (ldt + 1); b.strideC = 2 * s * (ldx + 1);
+    if (ws && ws_count && b.K >= 512) { b.splitk = (int)std::min<int64_t>(8, b.K / 128); b.ws = ws; b.ws_count = ws_count; }
+    return gemm_f64(stream, false, false, b);
+}
+
 int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv, int64_t ldd, double* X,
-                int64_t ldx, double* T, int64_t ldt, int max_block) {
+                int64_t ldx, double* T, int64_t ldt, int max_block, double* ws, int* ws_count) {
     if (n <= 0) return GPIRT_B200_OK;
     const int64_t stop = max_block > 0 ? std::min<int64_t>(n, max_block) : n;
-    GP_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * n * sizeof(double), stream));
+    // the n x n square only: X may be a diagonal block of a larger matrix
+    GP_CUDA(cudaMemset2DAsync(X, (size_t)ldx * sizeof(double), 0, (size_t)n * sizeof(double), (size_t)n, stream));
     {
         dim3 grid((unsigned)n, (unsigned)ceil_div(n, 128));
         GP_LAUNCH(k_scatter_block_inverses, grid, 128, 0, stream, Dinv, ldd, n, X, ldx);
@@ -252,26 +273,37 @@ int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const 
         const int full_pairs = (int)(n / (2 * s));           // pairs whose second block is complete
         const int64_t o_r = (int64_t)full_pairs * 2 * s;     // offset of a possible ragged pair
         const int s2 = (int)std::min<int64_t>(s, n - (o_r + s));   // size of its second block (<= 0: none)
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool ragged = pass == 1;
-            if (!ragged && full_pairs == 0) continue;
-            if (ragged && s2 <= 0) continue;
-            const int64_t o = ragged ? o_r : 0;
-            const int rows = ragged ? s2 : (int)s;
-            GemmArgs a;   // T21 = L21 X11   (X11 lower triangular)
-            a.M = rows; a.N = (int)s; a.K = (int)s;
-            a.A = L + (o + s) + o * ldl; a.lda = ldl; a.B = X + o + o * ldx; a.ldb = ldx;
-            a.C = T + (o + s) + o * ldt; a.ldc = ldt; a.tri = TRI_B_LOWER;
-            a.batch = ragged ? 1 : full_pairs;
-            a.strideA = 2 * s * (ldl + 1); a.strideB = 2 * s * (ldx + 1); a.strideC = 2 * s * (ldt + 1);
-            GP_TRY(gemm_f64(stream, false, false, a));
-            GemmArgs b;   // X21 = -X22 T21  (X22 lower triangular)
-            b.M = rows; b.N = (int)s; b.K = rows;
-            b.A = X + (o + s) + (o + s) * ldx; b.lda = ldx; b.B = T + (o + s) + o * ldt; b.ldb = ldt;
-            b.C = X + (o + s) + o * ldx; b.ldc = ldx; b.alpha = -1.0; b.tri = TRI_A_LOWER;
-            b.batch = a.batch; b.strideA = 2 * s * (ldx + 1); b.strideB = 2 * s * (ldt + 1); b.strideC = 2 * s * (ldx + 1);
-            GP_TRY(gemm_f64(stream, false, false, b));
+        if (full_pairs > 0) GP_TRY(trtri_merge(stream, L, ldl, X, ldx, T, ldt, 0, s, (int)s, full_pairs, ws, ws_count));
+        if (s2 > 0) GP_TRY(trtri_merge(stream, L, ldl, X, ldx, T, ldt, o_r, s, s2, 1, ws, ws_count));
+    }
+    return GPIRT_B200_OK;
+}
+
+__global__ void k_copy_block_inverse(const double* __restrict__ Dinv, int64_t ldd, int nb, double* __restrict__ X, int64_t ldx) {
+    const int r = threadIdx.x, c = blockIdx.x;   // one 128 x 128 diagonal block (strict upper of Dinv is zero)
+    if (r < nb && c < nb) X[r + (int64_t)c * ldx] = Dinv[r + (int64_t)c * ldd];
+}
+
+int trtri_lower_step(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv, int64_t ldd, double* X,
+                     int64_t ldx, double* T, int64_t ldt, int max_block, int k, double* ws, int* ws_count) {
+    const int nblk = (int)ceil_div(n, CHOL_NB);
+    if (k < 0 || k >= nblk) return GPIRT_B200_OK;
+    const int64_t k0 = (int64_t)k * CHOL_NB;
+    const int nb = (int)std::min<int64_t>(CHOL_NB, n - k0);
+    GP_LAUNCH(k_copy_block_inverse, (unsigned)nb, CHOL_NB, 0, stream, Dinv + k0, ldd, nb, X + k0 * (ldx + 1), ldx);
+    GP_CUDA(cudaGetLastError());
+    const int64_t stop = max_block > 0 ? std::min<int64_t>(n, max_block) : n;
+    const int64_t done = k0 + nb;                        // rows / columns of L that are final
+    for (int64_t s = CHOL_NB; s < stop; s *= 2) {
+        if (done % (2 * s) == 0) {                       // panel k completes a full pair of order-s blocks
+            GP_TRY(trtri_merge(stream, L, ldl, X, ldx, T, ldt, done - 2 * s, s, (int)s, 1, ws, ws_count));
+            continue;
         }
+        if (k != nblk - 1) break;                        // higher levels are not complete either
+        // last panel: the ragged pair of this level, if any (its second block is shorter than s; lower levels are done)
+        const int64_t o_r = (n / (2 * s)) * 2 * s;
+        const int64_t s2 = std::min<int64_t>(s, n - (o_r + s));
+        if (s2 > 0) GP_TRY(trtri_merge(stream, L, ldl, X, ldx, T, ldt, o_r, s, (int)s2, 1, ws, ws_count));
     }
     return GPIRT_B200_OK;
 }

@@ -37,7 +37,17 @@ int potrf_lower_rl(cudaStream_t stream, double* A, int64_t lda, int n, double* D
 //   inv([[L11,0],[L21,L22]]) = [[X11,0],[-X22 L21 X11, X22]], all pairs of one level in a single batched GEMM launch.
 // T is n x n scratch.  max_block > 0 (a power-of-two multiple of 128) stops the doubling there: X then holds the inverses of
 // the max_block x max_block diagonal blocks of L only (zeros elsewhere) — the leaf blocks of a coarser substitution.
+// splitk_ws / splitk_count (optional): workspace of the deterministic split-K of gemm_f64 — products with K >= 512 are
+// split min(8, K / 128) ways (the late levels are a few tiles with a long K).
 int trtri_lower(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv128, int64_t ldd, double* X,
-                int64_t ldx, double* T, int64_t ldt, int max_block = 0);
+                int64_t ldx, double* T, int64_t ldt, int max_block = 0, double* splitk_ws = nullptr, int* splitk_count = nullptr);
+
+// The same block inverses built PROGRESSIVELY behind a right-looking factorisation: call once per finished panel k
+// (k = 0 .. nblk-1 in order, on one stream).  Step k copies the 128-block inverse of panel k into X and merges every pair
+// of diagonal blocks of order 128, 256, ... < max_block that panel k completes (binary-counter pattern), so that after
+// the last panel only the merges that involve it remain: one pair per level.  X must be zero outside the written blocks
+// (zero it once; the written pattern is the same for every factorisation of the same order).
+int trtri_lower_step(cudaStream_t stream, const double* L, int64_t ldl, int n, const double* Dinv128, int64_t ldd, double* X,
+                     int64_t ldx, double* T, int64_t ldt, int max_block, int k, double* splitk_ws, int* splitk_count);
 
 }  // namespace gpirt

@@ -85,7 +85,14 @@ struct gpirt_b200_sampler {
     bool nu_ready = false;       // nu already holds L z for sweep nu_sweep
     uint32_t nu_sweep = 0;
     bool solve_ready = false;    // kstar already holds S^-1 K* and s the predictive sd for the current theta (ev_solve)
-    cudaEvent_t ev_linv = nullptr, ev_solve = nullptr;
+    cudaEvent_t ev_linv = nullptr, ev_solve = nullptr, ev_fwd = nullptr;
+    // The K* solves of the NEXT sweep depend on theta and the factor only.  rebuild_pipelined leaves them pending and the
+    // next sweep starts them on a side stream right before its ESS, so that they run beside it — and so that every side
+    // stream is joined at the end of a sweep, which is what lets the whole pipelined sweep be captured as a CUDA graph.
+    //   1: backward substitution of this rank's grid columns (the forward steps trailed the panels)   2: through L^-1
+    int deferred = 0;
+    int pipe_mask = 7;           // GPIRT_PIPE_MASK (debugging): 1 LZ, 2 beta / fill, 4 solves on their own streams
+    int launch_deferred_solves();
     int fstar_solves(cudaStream_t st);
     // solve_mode 1 (default with items sharded over GPUs): the two triangular solves for this rank's slice of the grid
     // columns as blocked substitutions with the 128-block inverses of the factorisation — no L^-1.  The forward steps
@@ -101,7 +108,12 @@ struct gpirt_b200_sampler {
     }
     int trsm_kstar(cudaStream_t st);
     int trsm_fwd_step(cudaStream_t st, int k);
-    int trsm_bwd(cudaStream_t st);
+    int trsm_bwd(cudaStream_t st, bool leading_blocks_inverted = false);
+    int bwd_block() const;                 // order of the diagonal-block inverses the backward substitution runs on
+    int invert_bwd_step(cudaStream_t st, int k);
+    double* splitk_ws = nullptr;           // partial tiles of the split-K products of the backward pass (thin: few grid columns per rank)
+    int* splitk_count = nullptr;
+    GemmArgs thin(GemmArgs a) const;
     int gather_solves(cudaStream_t st);
     bool has_missing = false;
     int ess_shape = -1, beta_shape = -1;   // ItemShape the last ESS / beta launch picked (gpirt_b200_sampler_uses)
@@ -155,10 +167,19 @@ struct gpirt_b200_sampler {
         cudaEventRecord(cur.b, stream);
         pending.push_back(cur);
     }
+    // GPIRT_TRACE=<file>: every timed segment is also written as "timer start_ms end_ms" relative to the sampler's
+    // creation (segments of different streams overlap: this is the timeline the per-timer sums cannot show)
+    cudaEvent_t trace_ref = nullptr;
+    FILE* trace_file = nullptr;
     void flush_timers() {  // call after ALL of the sampler's streams have been synchronised
         for (auto& sg : pending) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, sg.a, sg.b) == cudaSuccess) { ms[sg.timer] += t; calls[sg.timer] += 1; }
+            if (trace_file && trace_ref) {
+                float t0 = 0.f, t1 = 0.f;
+                if (cudaEventElapsedTime(&t0, trace_ref, sg.a) == cudaSuccess && cudaEventElapsedTime(&t1, trace_ref, sg.b) == cudaSuccess)
+                    fprintf(trace_file, "%d %.4f %.4f\n", sg.timer, t0, t1);
+            }
             pool.push_back(sg.a); pool.push_back(sg.b);
         }
         pending.clear();
@@ -179,6 +200,10 @@ struct gpirt_b200_sampler {
     uint32_t* d_sweep = nullptr;          // device copy of the sweep counter read by the captured kernels
     uint32_t d_sweep_value = 0xffffffffu; // what *d_sweep holds (host mirror)
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // [accumulate_irf]
+    int64_t graph_replays = 0;            // sweeps run as a graph launch (gpirt_b200_sampler_uses(s, 5))
+    bool graph_pipelined = false;         // the captured sweep is the pipelined one (side streams forked and joined inside the graph)
+    int graph_deferred = 0;
+    void drop_graphs() { for (auto& g : gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; } }
     int64_t graph_kernels = 0;            // kernels per sweep (counted on the eager path; a graph replay launches the same ones)
     int sweep_eager(uint32_t t, int accumulate);
     int sweep_graph(uint32_t t, int accumulate);
@@ -252,6 +277,10 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_TRY(comm_init(comm, opts.rank, opts.world_size, opts.nccl_unique_id));
     }
     launches_at_create = g_launch_count;
+    if (const char* tf = getenv("GPIRT_TRACE")) {
+        if (opts.rank == 0 || opts.world_size <= 1) trace_file = fopen(tf, "a");
+        if (trace_file) fprintf(trace_file, "# sampler %d x %d world %d\n", n, m, opts.world_size > 1 ? opts.world_size : 1);
+    }
     {   // the factorisation chain and its bulk updates run at the highest priority, the overlapped L Z product at the lowest
         int least = 0, greatest = 0;
         GP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -259,8 +288,11 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_CUDA(cudaStreamCreateWithPriority(&lookahead.aux, cudaStreamNonBlocking, greatest));
         GP_CUDA(cudaStreamCreateWithPriority(&st_beta, cudaStreamNonBlocking, least));
         GP_CUDA(cudaStreamCreateWithPriority(&st_lz, cudaStreamNonBlocking, least));
-        GP_CUDA(cudaStreamCreateWithPriority(&st_trsm, cudaStreamNonBlocking, greatest));
-        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        // the substitution steps that trail the panels yield to the chain itself
+        GP_CUDA(cudaStreamCreateWithPriority(&st_trsm, cudaStreamNonBlocking, greatest < least ? greatest + 1 : greatest));
+        for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_fwd}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        if (const char* pm = getenv("GPIRT_PIPE_MASK")) pipe_mask = atoi(pm);
+        if (trace_file) { GP_CUDA(cudaEventCreate(&trace_ref)); GP_CUDA(cudaEventRecord(trace_ref, stream)); }
         const char* sm = getenv("GPIRT_SOLVE_MODE");
         // through L^-1 (n^3/3 for the inverse + two triangular products) or by blocked substitution behind the Cholesky panels
         // (2 n^2 x 1001): substitution wins when few right-hand sides are left per rank, and on one GPU once n/3 > 2 x 1001
@@ -289,6 +321,17 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
     GP_TRY(alloc(f, nm)); GP_TRY(alloc(Z, nm)); GP_TRY(alloc(nu, nm));
     GP_TRY(alloc(fstar, Nm)); GP_TRY(alloc(Dmat, Nm)); GP_TRY(alloc(irf_sum, Nm));
     GP_TRY(alloc(kstar, (size_t)ldn * kcols)); GP_TRY(alloc(s, std::max((size_t)ldN, kcols)));
+    if (solve_mode == 1) {
+        // split-K workspace: the thin products of the backward pass (M <= 4096 rows x this rank's grid columns, 8 splits) and
+        // the batched late levels of the block inverses (n / 1024 pairs of 512 x 512 tiles, 4 splits)
+        const size_t per = (size_t)ceil_div(N_GRID, comm.world);
+        const size_t ws_doubles = std::max((size_t)round_up(std::min(n, 4096), 128) * (size_t)round_up((int64_t)per, 128) * 8, (size_t)n * 1024);
+        const size_t ws_tiles = std::max((size_t)ceil_div(std::min(n, 4096), 64) * (size_t)ceil_div((int64_t)per, 64), (size_t)n / 8) + 64;
+        GP_TRY(alloc(splitk_ws, ws_doubles));
+        GP_TRY(alloc(splitk_count, ws_tiles));
+        GP_CUDA(cudaMemsetAsync(splitk_count, 0, ws_tiles * sizeof(int), stream));
+        GP_CUDA(cudaMemsetAsync(Linv, 0, (size_t)ldn * n * sizeof(double), stream));   // block inverses: only their lower parts are rewritten
+    }
     GP_TRY(alloc(logPt, (size_t)ldN * (n + 1))); GP_TRY(alloc(partial, (size_t)N_CHUNKS * N_GRID));
     GP_TRY(alloc(nprop, (size_t)m)); GP_TRY(alloc(theta_idx, (size_t)n)); GP_TRY(alloc(status, 4)); GP_TRY(alloc(counters, 2)); GP_TRY(alloc(work, 4));
     GP_TRY(alloc(d_sweep, 2));
@@ -436,29 +479,57 @@ int gpirt_b200_sampler::trsm_fwd_step(cudaStream_t st, int k) {
 // s from tmp = L^-1 K* (:20), then the backward substitution  L^T A = tmp  (tmp = kstar2 is consumed, A -> kstar)    :24
 // The backward pass cannot trail the factorisation (it starts at the last block), so it is the serial tail of the sharded
 // sweep: instead of 32 steps with the 128-blocks it runs with the inverses of 1024 x 1024 diagonal blocks (built from the
-// 128-block inverses by three levels of batched recursive doubling, ~3 GFLOP) — 4 steps of two large products each.
-int gpirt_b200_sampler::trsm_bwd(cudaStream_t st) {
+// 128-block inverses by three levels of batched recursive doubling) — 4 steps of two products each.  With a handful of
+// grid columns per rank those products are thin (126 columns at 8 GPUs: 32 output tiles, K = 1024), so they are split
+// over K (deterministic split-K, gemm_f64.cuh); and every diagonal-block inverse but the last is computed behind the
+// factorisation (invert_bwd_block from the panel hook), which leaves one block inverse and seven short products in the tail.
+int gpirt_b200_sampler::bwd_block() const {
+    static const int forced = getenv("GPIRT_BWD_BLOCK") ? atoi(getenv("GPIRT_BWD_BLOCK")) : 0;
+    int blk = forced > 0 ? forced : (n >= 2048 ? 1024 : (n >= 1024 ? 512 : CHOL_NB));
+    if (blk % CHOL_NB != 0 || (blk & (blk - 1)) != 0) blk = CHOL_NB;
+    return blk;
+}
+// the split factor depends on the shape of the product's A operand only — never on the number of right-hand sides, i.e.
+// on how many ranks share the grid columns: a sharded run stays bit-identical to the unsharded one
+GemmArgs gpirt_b200_sampler::thin(GemmArgs a) const {
+    static const bool off = getenv("GPIRT_SPLITK") && atoi(getenv("GPIRT_SPLITK")) == 0;
+    if (!off && splitk_ws && a.K >= 512 && a.M <= 4096) {
+        a.splitk = (int)std::min<int64_t>(8, a.K / 128);
+        a.ws = splitk_ws;
+        a.ws_count = splitk_count;
+    }
+    return a;
+}
+// the inverses of the diagonal blocks of order bwd_block() grow on the diagonal of Linv behind the factorisation: step k
+// (after panel k) adds the 128-block inverse of panel k and every merge that panel completes (trtri_lower_step)
+int gpirt_b200_sampler::invert_bwd_step(cudaStream_t st, int k) {
+    const int blk = bwd_block();
+    if (blk <= CHOL_NB) return GPIRT_B200_OK;
+    return trtri_lower_step(st, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn, blk, k, splitk_ws, splitk_count);
+}
+int gpirt_b200_sampler::trsm_bwd(cudaStream_t st, bool leading_blocks_inverted) {
     int c0, nc;
     grid_slice(c0, nc);
     if (nc <= 0) return GPIRT_B200_OK;
     double* A = kstar + (int64_t)c0 * ldn;
     double* Y = kstar2 + (int64_t)c0 * ldn;
     GP_TRY(launch_fstar_sd(st, Y, ldn, n, nc, s + c0));
-    static const int forced = getenv("GPIRT_BWD_BLOCK") ? atoi(getenv("GPIRT_BWD_BLOCK")) : 0;
-    int blk = forced > 0 ? forced : (n >= 2048 ? 1024 : (n >= 1024 ? 512 : CHOL_NB));
-    if (blk % CHOL_NB != 0 || (blk & (blk - 1)) != 0) blk = CHOL_NB;
+    const int blk = bwd_block();
+    const int nblk = (int)ceil_div(n, blk);
     const double* Xb = Dinv;       // leaf inverses: block k at rows k * blk of an n x blk array ...
     int64_t ldx = ldn, diag_step = 0;
     if (blk > CHOL_NB) {           // ... or on the diagonal of Linv (n x n)
-        GP_TRY(trtri_lower(st, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn, blk));
+        Seg sg = tic_on(GPIRT_B200_T_TRTRI, st);
+        if (leading_blocks_inverted) GP_TRY(invert_bwd_step(st, (int)ceil_div(n, CHOL_NB) - 1));   // only the merges the last panel completes
+        else GP_TRY(trtri_lower(st, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn, blk, splitk_ws, splitk_count));
+        toc_on(sg, st);
         Xb = Linv; diag_step = ldn;
     }
-    const int nblk = (int)ceil_div(n, blk);
     for (int k = nblk - 1; k >= 0; --k) {
         const int r0 = k * blk, nb = std::min(blk, n - r0);
-        GP_TRY(gemm_f64(st, true, false, G(nb, nc, nb, Xb + r0 + (int64_t)r0 * diag_step, ldx, Y + r0, ldn, A + r0, ldn, 1.0, 0.0, TRI_A_UPPER)));
+        GP_TRY(gemm_f64(st, true, false, thin(G(nb, nc, nb, Xb + r0 + (int64_t)r0 * diag_step, ldx, Y + r0, ldn, A + r0, ldn, 1.0, 0.0, TRI_A_UPPER))));
         if (r0 > 0)
-            GP_TRY(gemm_f64(st, true, false, G(r0, nc, nb, L + r0, ldn, A + r0, ldn, Y, ldn, -1.0, 1.0, TRI_NONE)));
+            GP_TRY(gemm_f64(st, true, false, thin(G(r0, nc, nb, L + r0, ldn, A + r0, ldn, Y, ldn, -1.0, 1.0, TRI_NONE))));
     }
     return GPIRT_B200_OK;
 }
@@ -634,10 +705,9 @@ int gpirt_b200_sampler::ess_only(uint32_t sweep) {
 //   stream  : K(theta,theta)+1e-3 I, right-looking Cholesky chain (+ its bulk stream), L^-1
 //   st_lz   : after every lz_group finished block columns  nu[r0:, :] (+)= L[r0:, r0:r1] Z[r0:r1, :]
 int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
-    static const int mask = getenv("GPIRT_PIPE_MASK") ? atoi(getenv("GPIRT_PIPE_MASK")) : 7;   // debugging: 1 LZ, 2 beta/fill, 4 solves
+    const int mask = pipe_mask;
     cudaStream_t st_beta = (mask & 2) ? this->st_beta : stream;
     cudaStream_t st_lz = (mask & 1) ? this->st_lz : stream;
-    cudaStream_t st_solve = (mask & 4) ? this->st_lz : stream;
     GP_CUDA(cudaEventRecord(ev_theta, stream));
     GP_CUDA(cudaStreamWaitEvent(st_beta, ev_theta, 0));
     {
@@ -666,12 +736,26 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         toc_on(a, st_trsm);
     }
     bool first = true;
-    int lz_slice = 0, lz_prev_end = 0, lz_next_end = lz_group;
+    // Slices of the overlapped product.  Through L^-1 (one GPU): equal slices of lz_group panels — what is left after the
+    // last panel runs under the inversion.  Substitution route (items sharded): nothing hides the remainder, so the
+    // slices shrink towards the end (half of the panels, all but an eighth, the rest: ~1.5 % of the product is left).
+    // The schedule may depend on the route but never on the sharding itself: the slices are added in FP64, so their
+    // boundaries are part of the rounding of nu, and a sharded run must reproduce the unsharded one bit for bit.
+    const int nblk_all = (int)ceil_div(n, CHOL_NB);
+    static const bool lz_uniform = getenv("GPIRT_LZ_GROUP") != nullptr;   // developer override: equal slices of lz_group panels
+    auto next_end = [&](int e) {
+        if (lz_uniform || !use_i8gemm || !trsm_route) return min(nblk_all, e + lz_group);
+        if (e < nblk_all / 2) return max(1, nblk_all / 2);
+        const int tail_start = nblk_all - max(1, nblk_all / 8);
+        return e < tail_start ? tail_start : nblk_all;
+    };
+    int lz_slice = 0, lz_prev_end = 0, lz_next_end = next_end(0);
     lookahead.after_panel = [&](int k, int nblk, cudaEvent_t done) -> int {
         if (trsm_route) {   // forward substitution step k trails panel k
             GP_CUDA(cudaStreamWaitEvent(st_trsm, done, 0));
             Seg sg = tic_on(GPIRT_B200_T_TRSM, st_trsm);
             GP_TRY(trsm_fwd_step(st_trsm, k));
+            if (k != nblk - 1) GP_TRY(invert_bwd_step(st_trsm, k));   // block inverses of the backward pass grow behind the panels
             toc_on(sg, st_trsm);
         }
         // a slice of the product ends after every lz_group panels.  (Shrinking the later slices geometrically so that less of
@@ -681,7 +765,7 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         const int g = lz_slice++;
         const int r0 = lz_prev_end * CHOL_NB, r1 = min(n, (k + 1) * CHOL_NB);
         lz_prev_end = k + 1;
-        lz_next_end = min(nblk, lz_prev_end + lz_group);
+        lz_next_end = next_end(lz_prev_end);
         if (first) {
             GP_CUDA(cudaStreamWaitEvent(st_lz, ev_z, 0));
             first = false;
@@ -711,18 +795,32 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         tic(GPIRT_B200_T_TRTRI);
         GP_TRY(trtri_lower(stream, L, ldn, n, Dinv, ldn, Linv, ldn, Tmp, ldn));
         toc();
-    } else {   // backward substitution behind the last forward step; the next sweep's ESS does not wait for it
-        Seg sg = tic_on(GPIRT_B200_T_TRSM, st_trsm);
-        GP_TRY(trsm_bwd(st_trsm));
-        toc_on(sg, st_trsm);
-        GP_CUDA(cudaEventRecord(ev_solve, st_trsm));
-        local_solve_ready = true;
+    } else {   // the forward steps join here; the backward substitution starts with the next sweep, beside its ESS
+        GP_CUDA(cudaEventRecord(ev_fwd, st_trsm));
+        GP_CUDA(cudaStreamWaitEvent(stream, ev_fwd, 0));
+        deferred = 1;
     }
     GP_CUDA(cudaStreamWaitEvent(stream, ev_lz, 0));
     GP_CUDA(cudaStreamWaitEvent(stream, ev_beta, 0));
     nu_ready = true;
     nu_sweep = next_sweep;
-    if (opts.fstar_mode == 0 && comm.world <= 1 && !trsm_route) {   // the next sweep's K* solves run beside its ESS (they need theta and L^-1 only)
+    if (opts.fstar_mode == 0 && comm.world <= 1 && !trsm_route) deferred = 2;   // K* solves through L^-1, beside the next ESS
+    return GPIRT_B200_OK;
+}
+
+int gpirt_b200_sampler::launch_deferred_solves() {
+    const int what = deferred;
+    deferred = 0;
+    if (what == 1) {
+        GP_CUDA(cudaEventRecord(ev_linv, stream));
+        GP_CUDA(cudaStreamWaitEvent(st_trsm, ev_linv, 0));
+        Seg sg = tic_on(GPIRT_B200_T_TRSM, st_trsm);
+        GP_TRY(trsm_bwd(st_trsm, true));
+        toc_on(sg, st_trsm);
+        GP_CUDA(cudaEventRecord(ev_solve, st_trsm));
+        local_solve_ready = true;
+    } else if (what == 2) {
+        cudaStream_t st_solve = (pipe_mask & 4) ? st_lz : stream;
         GP_CUDA(cudaEventRecord(ev_linv, stream));
         GP_CUDA(cudaStreamWaitEvent(st_solve, ev_linv, 0));
         GP_TRY(fstar_solves(st_solve));
@@ -736,6 +834,7 @@ __global__ void k_bump_sweep(uint32_t* sweep) { *sweep += 1u; }
 
 int gpirt_b200_sampler::sweep_eager(uint32_t t, int accumulate) {
     const bool can_pipe = pipeline && ceil_div(n, CHOL_NB) > 2;   // the look-ahead factorisation needs > 2 panels
+    if (deferred) GP_TRY(launch_deferred_solves());
     if (can_pipe && nu_ready && nu_sweep == t) GP_TRY(ess_only(t));
     else GP_TRY(step_draw_f(t));
     nu_ready = false;
@@ -764,10 +863,12 @@ int gpirt_b200_sampler::sweep_graph(uint32_t t, int accumulate) {
             GP_LAUNCH(k_bump_sweep, 1, 1, 0, stream, d_sweep);
             rc = sweep_eager(t, accumulate);
             e = cudaStreamEndCapture(stream, &graph);
+            graph_pipelined = pipeline && ceil_div(n, CHOL_NB) > 2;
+            graph_deferred = deferred;
         }
         capturing = false;
         g_launch_count = counted;
-        if (rc == GPIRT_B200_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec[a], graph, 0);
+        if (rc == GPIRT_B200_OK && e == cudaSuccess) e = cudaGraphInstantiateWithFlags(&gexec[a], graph, cudaGraphInstantiateFlagUseNodePriority);   // per-node priorities = the priorities of the captured streams
         if (graph) cudaGraphDestroy(graph);
         if (rc != GPIRT_B200_OK || e != cudaSuccess) {   // not capturable on this driver: stay on the eager path for good
             cudaGetLastError();
@@ -782,16 +883,24 @@ int gpirt_b200_sampler::sweep_graph(uint32_t t, int accumulate) {
     }
     GP_CUDA(cudaGraphLaunch(gexec[a], stream));
     g_launch_count += graph_kernels;   // the kernels inside the graph still launch
+    graph_replays += 1;
     d_sweep_value = t;
+    if (graph_pipelined) {             // the host-side state a pipelined sweep leaves behind
+        nu_ready = true; nu_sweep = t + 1;
+        deferred = graph_deferred;
+        solve_ready = local_solve_ready = false;
+    }
     return GPIRT_B200_OK;
 }
 
 int gpirt_b200_sampler::sweep(int accumulate) {
     const uint32_t t = ++sweep_counter;
     const bool can_pipe = pipeline && ceil_div(n, CHOL_NB) > 2;
-    // graph replay only for the un-pipelined sweep, without per-step timers, on one GPU, and after one eager sweep has
-    // done every lazy first-use initialisation (function attributes, occupancy queries, the softplus table)
-    if (graph_enabled && !can_pipe && !timing && comm.world <= 1 && warmed && opts.fstar_mode == 0) return sweep_graph(t, accumulate);
+    // graph replay without per-step timers, after one eager sweep has done every lazy first-use initialisation (function
+    // attributes, occupancy queries, the softplus table); the pipelined sweep only in its steady state (proposals and
+    // solves prepared by the previous sweep), which is the state the captured launch sequence assumes
+    const bool steady = !can_pipe || (nu_ready && nu_sweep == t && deferred != 0);
+    if (graph_enabled && !timing && warmed && opts.fstar_mode == 0 && steady) return sweep_graph(t, accumulate);
     const int64_t before = g_launch_count;
     GP_TRY(sweep_eager(t, accumulate));
     graph_kernels = g_launch_count - before;
@@ -810,12 +919,14 @@ void gpirt_b200_sampler::destroy() {
     lookahead.ev_panel.clear(); lookahead.ev_bulk.clear();
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
     for (cudaStream_t* q : {&st_beta, &st_lz, &st_trsm}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
-    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_fwd}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    if (trace_file) { fclose(trace_file); trace_file = nullptr; }
+    if (trace_ref) { cudaEventDestroy(trace_ref); trace_ref = nullptr; }
     comm_destroy(comm);
     ti8.destroy();
     dp_L.destroy(); dp_A.destroy(); dp_B.destroy(); dp_Linv.destroy(); dp_LinvT.destroy(); dp_K.destroy();
     void* ptrs[] = {d_sweep, work, y8, yd, theta, theta_star, prior, beta, pm, psd, pstep, L, Dinv, f, Z, nu, fstar, Dmat, irf_sum,
-                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, chol_flags};
+                    kstar, s, logPt, partial, nprop, theta_idx, status, counters, Linv, Tmp, kstar2, chol_flags, splitk_ws, splitk_count};
     for (void* p : ptrs) pool_free(p, stream);
     if (stream) cudaStreamSynchronize(stream);
     if (stream) cudaStreamDestroy(stream);
@@ -977,6 +1088,7 @@ int gpirt_b200_sampler_sweep(gpirt_b200_sampler* s, int n_sweeps, int accumulate
 int gpirt_b200_sampler_step(gpirt_b200_sampler* s, int step, uint32_t sweep) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->nu_ready = false;
+    s->deferred = 0;
     if (s->solve_ready || s->local_solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = s->local_solve_ready = false; }
     int rc;
     switch (step) {
@@ -1041,6 +1153,7 @@ int gpirt_b200_sampler_set(gpirt_b200_sampler* s, int field, const double* host_
     double* dev; int64_t ld; int rows, cols;
     if (field_shape(s, field, &dev, &ld, &rows, &cols)) return GPIRT_B200_ERR_ARG;
     s->nu_ready = false;
+    s->deferred = 0;
     if (s->solve_ready || s->local_solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = s->local_solve_ready = false; }
     GP_TRY(upload_padded(dev, ld, host_in, rows, cols, s->stream));
     GP_CUDA(cudaStreamSynchronize(s->stream));
@@ -1066,7 +1179,9 @@ int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled) {
 int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled) {
     if (!s) return GPIRT_B200_ERR_ARG;
     s->pipeline = enabled != 0;
+    s->drop_graphs();
     s->nu_ready = false;
+    s->deferred = 0;
     if (s->solve_ready || s->local_solve_ready) { cudaStreamWaitEvent(s->stream, s->ev_solve, 0); s->solve_ready = s->local_solve_ready = false; }
     return GPIRT_B200_OK;
 }
@@ -1079,6 +1194,7 @@ int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature) {
     if (feature == 2) return s->ess_shape;
     if (feature == 3) return s->beta_shape;
     if (feature == 4) return s->solve_mode;
+    if (feature == 5) return (int)std::min<int64_t>(s->graph_replays, INT_MAX);
     return -1;
 }
 

@@ -142,8 +142,8 @@ int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s); /* kernels launched 
 /* which code path this sampler selected (bench.py picks the roofline denominator by it, the parity tests assert it):
  * feature 0 = int8 theta contraction (1/0), 1 = fixed-point (int8) L Z / f* / K*-solve products (1/0),
  * 2 / 3 = launch shape of the last ESS / beta step (0 one CTA per item, 1 persistent CTAs, 2 streaming shape for
- * n > 4096; -1 before the first launch), 4 = K*-solve route (0 through L^-1, 1 blocked substitution);
- * -1 for an unknown feature */
+ * n > 4096; -1 before the first launch), 4 = K*-solve route (0 through L^-1, 1 blocked substitution), 5 = number of
+ * sweeps so far that ran as ONE CUDA-graph launch; -1 for an unknown feature */
 int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature);
 void gpirt_b200_sampler_destroy(gpirt_b200_sampler* s);
 

@@ -377,6 +377,32 @@ def test_chain_blocked_substitution_solves_match_inverse_route(G, O, n, m, monke
         assert np.max(np.abs(a["IRFs"] - want["IRFs"])) <= 1e-7
 
 
+@pytest.mark.parametrize("n,m,route", [(100, 60, "0"), (640, 300, "0"), (640, 300, "1"), (1152, 260, "1")])
+def test_graph_replayed_sweeps_equal_eager_sweeps(G, n, m, route, monkeypatch):
+    """With the per-step timers off every sweep after the first is ONE CUDA-graph launch — captured from the very launch
+    sequence of the eager sweep, for n > 256 the pipelined one with its five streams forked and joined inside the graph
+    (stream priorities carried as per-node launch attributes).  Same kernels, same addressed RNG: the state after 6 sweeps
+    must be bit-identical to 6 eager sweeps, on both K*-solve routes."""
+    from gpirt_b200 import _lib
+    monkeypatch.setenv("GPIRT_SOLVE_MODE", route)
+    prob = make_problem(n, m, seed=n + 3, missing=0.03)
+    state = {}
+    for use_graph in (0, -1):
+        s = G.Sampler(prob["y"], prob["theta"], prob["pm"], prob["psd"], prob["pstep"], seed=77, use_graph=use_graph)
+        s.set_timing(False)
+        s.init_draws()
+        s.sweep(4)
+        s.sweep(2, accumulate_irf=True)
+        assert s.uses(4) == int(route)
+        replays = s.uses(5)
+        assert (replays >= 4) if use_graph == 0 else (replays == 0), "graph replay must be the path that ran (or not)"
+        state[use_graph] = {k: s.get(f) for k, f in (("theta", _lib.THETA), ("beta", _lib.BETA), ("f", _lib.F), ("fstar", _lib.FSTAR),
+                                                      ("irf", _lib.IRF_SUM), ("L", _lib.CHOL))}
+        s.close()
+    for k in state[0]:
+        assert np.array_equal(state[0][k], state[-1][k]), k
+
+
 def test_senate116_short_chain(G, O):
     import warnings
     import gpirt_b200
