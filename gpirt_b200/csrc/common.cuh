@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <climits>
 #include <cstdint>
 #include <mutex>
 #include <utility>
@@ -64,6 +65,14 @@ struct DeviceOnce {
 // stream anyway, but a kernel node CAPTURED into a CUDA graph keeps only what the launch itself says — without it the
 // replayed sweep runs the Cholesky chain at the same priority as the bulk products it is supposed to overtake.
 extern std::atomic<int64_t> g_launch_count;
+// priority for the launches of the calling thread instead of their stream's (INT_MIN: none): lets ONE kernel of a stream
+// yield to a side stream of equal priority (the ESS beside the backward substitution, sampler.cu)
+extern thread_local int g_launch_priority_override;
+struct LaunchPriority {
+    int saved;
+    explicit LaunchPriority(int p) : saved(g_launch_priority_override) { g_launch_priority_override = p; }
+    ~LaunchPriority() { g_launch_priority_override = saved; }
+};
 template <typename... KArgs, typename... Args>
 inline void launch_with_stream_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -71,7 +80,8 @@ inline void launch_with_stream_priority(void (*kernel)(KArgs...), dim3 grid, dim
     cudaLaunchAttribute attr[1];
     int prio = 0;
     cfg.numAttrs = 0;
-    if (stream != nullptr && cudaStreamGetPriority(stream, &prio) == cudaSuccess) {
+    if (g_launch_priority_override != INT_MIN || (stream != nullptr && cudaStreamGetPriority(stream, &prio) == cudaSuccess)) {
+        if (g_launch_priority_override != INT_MIN) prio = g_launch_priority_override;
         attr[0].id = cudaLaunchAttributePriority;
         attr[0].val.priority = prio;
         cfg.attrs = attr;

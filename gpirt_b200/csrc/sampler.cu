@@ -27,6 +27,7 @@
 namespace gpirt {
 
 std::atomic<int64_t> g_launch_count{0};
+thread_local int g_launch_priority_override = INT_MIN;
 std::mutex& device_once_mutex() { static std::mutex mu; return mu; }
 static thread_local char g_last_error[512] = "";
 void set_last_error(const char* fmt, ...) {
@@ -58,6 +59,14 @@ void pool_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 }  // namespace gpirt
 
 using namespace gpirt;
+
+// GPIRT_TRACE inside a captured sweep: CUDA events cannot be timed there, so the segment boundaries are tiny kernels that
+// store %globaltimer (ns) — they replay with the graph, and the last replay's stamps are written out with the trace
+__global__ void k_stamp(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
 
 struct gpirt_b200_sampler {
     int n = 0, m = 0;
@@ -91,6 +100,8 @@ struct gpirt_b200_sampler {
     // stream is joined at the end of a sweep, which is what lets the whole pipelined sweep be captured as a CUDA graph.
     //   1: backward substitution of this rank's grid columns (the forward steps trailed the panels)   2: through L^-1
     int deferred = 0;
+    int prio_second = 0;            // one notch below the top stream priority
+    bool tail_beside_ess = false;   // the backward pass was just started: the ESS that follows must leave it SMs
     int pipe_mask = 7;           // GPIRT_PIPE_MASK (debugging): 1 LZ, 2 beta / fill, 4 solves on their own streams
     int launch_deferred_solves();
     int fstar_solves(cudaStream_t st);
@@ -133,7 +144,24 @@ struct gpirt_b200_sampler {
     static constexpr int N_CHUNKS = 128;   // item chunks of the D row sums: enough CTAs to cover the HBM latency of the column walk
 
     // ---- timers ----
-    struct Seg { int timer; cudaEvent_t a, b; };
+    struct Seg { int timer; cudaEvent_t a, b; int slot = -1; };
+    unsigned long long* d_stamps = nullptr;       // 2 slots per traced segment of the captured sweep
+    std::vector<std::pair<int, int>> stamp_segs;  // (timer, first slot)
+    static constexpr int MAX_STAMPS = 4096;
+    bool stamping() const { return trace_file && capturing && d_stamps && (int)stamp_segs.size() * 2 + 2 <= MAX_STAMPS; }
+    void dump_stamps() {
+        if (!trace_file || !d_stamps || stamp_segs.empty()) return;
+        std::vector<unsigned long long> h(2 * stamp_segs.size());
+        if (cudaMemcpy(h.data(), d_stamps, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        unsigned long long t0 = ~0ull;
+        for (auto v : h) if (v && v < t0) t0 = v;
+        fprintf(trace_file, "# graph sweep (last replay) %d x %d\n", n, m);
+        for (auto& sg : stamp_segs) {
+            const unsigned long long a = h[sg.second], b = h[sg.second + 1];
+            if (a && b) fprintf(trace_file, "%d %.4f %.4f\n", sg.first, (a - t0) * 1e-6, (b - t0) * 1e-6);
+        }
+        fflush(trace_file);
+    }
     std::vector<Seg> pending;
     std::vector<cudaEvent_t> pool;
     double ms[GPIRT_B200_TIMER_COUNT] = {0};
@@ -142,12 +170,19 @@ struct gpirt_b200_sampler {
 
     Seg tic_on(int timer, cudaStream_t st) {
         Seg sg{timer, nullptr, nullptr};
+        if (stamping()) {
+            sg.slot = 2 * (int)stamp_segs.size();
+            stamp_segs.push_back({timer, sg.slot});
+            k_stamp<<<1, 1, 0, st>>>(d_stamps + sg.slot);
+            return sg;
+        }
         if (!timing || capturing) return sg;
         sg.a = get_event(); sg.b = get_event();
         cudaEventRecord(sg.a, st);
         return sg;
     }
     void toc_on(Seg& sg, cudaStream_t st) {
+        if (sg.slot >= 0) { k_stamp<<<1, 1, 0, st>>>(d_stamps + sg.slot + 1); return; }
         if (!timing || !sg.a) return;
         cudaEventRecord(sg.b, st);
         pending.push_back(sg);
@@ -158,11 +193,14 @@ struct gpirt_b200_sampler {
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
     void tic(int timer) {
+        if (stamping()) { cur = tic_on(timer, stream); return; }
+        cur.slot = -1;
         if (!timing || capturing) return;
         cur.timer = timer; cur.a = get_event(); cur.b = get_event();
         cudaEventRecord(cur.a, stream);
     }
     void toc() {
+        if (cur.slot >= 0) { toc_on(cur, stream); cur.slot = -1; return; }
         if (!timing || capturing) return;
         cudaEventRecord(cur.b, stream);
         pending.push_back(cur);
@@ -288,11 +326,16 @@ int gpirt_b200_sampler::create(const double* y, int64_t n_, int64_t m_, const do
         GP_CUDA(cudaStreamCreateWithPriority(&lookahead.aux, cudaStreamNonBlocking, greatest));
         GP_CUDA(cudaStreamCreateWithPriority(&st_beta, cudaStreamNonBlocking, least));
         GP_CUDA(cudaStreamCreateWithPriority(&st_lz, cudaStreamNonBlocking, least));
+        prio_second = greatest < least ? greatest + 1 : greatest;
         // the substitution steps that trail the panels yield to the chain itself
         GP_CUDA(cudaStreamCreateWithPriority(&st_trsm, cudaStreamNonBlocking, greatest < least ? greatest + 1 : greatest));
         for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_fwd}) GP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         if (const char* pm = getenv("GPIRT_PIPE_MASK")) pipe_mask = atoi(pm);
-        if (trace_file) { GP_CUDA(cudaEventCreate(&trace_ref)); GP_CUDA(cudaEventRecord(trace_ref, stream)); }
+        if (trace_file) {
+            GP_CUDA(cudaEventCreate(&trace_ref)); GP_CUDA(cudaEventRecord(trace_ref, stream));
+            GP_CUDA(cudaMalloc((void**)&d_stamps, MAX_STAMPS * sizeof(unsigned long long)));
+            GP_CUDA(cudaMemset(d_stamps, 0, MAX_STAMPS * sizeof(unsigned long long)));
+        }
         const char* sm = getenv("GPIRT_SOLVE_MODE");
         // through L^-1 (n^3/3 for the inverse + two triangular products) or by blocked substitution behind the Cholesky panels
         // (2 n^2 x 1001): substitution wins when few right-hand sides are left per rank, and on one GPU once n/3 > 2 x 1001
@@ -695,7 +738,14 @@ int gpirt_b200_sampler::init_draws() {
 // ESS with nu already in place (the product L z was accumulated behind the previous sweep's factorisation)
 int gpirt_b200_sampler::ess_only(uint32_t sweep) {
     tic(GPIRT_B200_T_ESS);
-    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1, work, &ess_shape));
+    // beside the backward substitution: one CTA per item instead of the persistent CTAs (which own every SM until the item
+    // queue is empty), so that the short kernels of the pass get SMs as item CTAs retire
+    // and one notch below the pass in priority: an item CTA takes the whole register file of its SM, and at equal priority
+    // the block scheduler drains the grid that was launched first — the pass would start when the ESS has ended
+    int* queue = tail_beside_ess ? nullptr : work;
+    LaunchPriority yield(tail_beside_ess ? prio_second : INT_MIN);
+    tail_beside_ess = false;
+    GP_TRY(launch_ess(stream, f, nu, ldn, y8, ldy8, theta, beta, n, m, key_at(sweep), item_offset, nprop, status + 1, queue, &ess_shape));
     toc();
     return GPIRT_B200_OK;
 }
@@ -736,15 +786,18 @@ int gpirt_b200_sampler::rebuild_pipelined(uint32_t sweep, uint32_t next_sweep) {
         toc_on(a, st_trsm);
     }
     bool first = true;
-    // Slices of the overlapped product.  Through L^-1 (one GPU): equal slices of lz_group panels — what is left after the
-    // last panel runs under the inversion.  Substitution route (items sharded): nothing hides the remainder, so the
-    // slices shrink towards the end (half of the panels, all but an eighth, the rest: ~1.5 % of the product is left).
+    // Slices of the overlapped product.  Through L^-1 (one GPU): equal slices of lz_group = 16 panels — every slice pays
+    // the fixed-point kernel's epilogue over all row tiles below it, and what is left after the last panel runs under the
+    // inversion.  Substitution route (items sharded): nothing hides the remainder, so the slices shrink towards the end
+    // (half of the panels, all but an eighth, the rest: ~1.5 % of the product is left behind the factorisation).  Eight
+    // equal slices of 4 panels were measured and lost (4.6 -> 5.2 ms per sweep on 4 GPUs): the early panels' bulk updates
+    // keep the whole GPU busy, and product slices that start there only delay the chain.
     // The schedule may depend on the route but never on the sharding itself: the slices are added in FP64, so their
     // boundaries are part of the rounding of nu, and a sharded run must reproduce the unsharded one bit for bit.
     const int nblk_all = (int)ceil_div(n, CHOL_NB);
-    static const bool lz_uniform = getenv("GPIRT_LZ_GROUP") != nullptr;   // developer override: equal slices of lz_group panels
+    static const bool lz_forced = getenv("GPIRT_LZ_GROUP") != nullptr;   // developer override: slices of lz_group panels on every route
     auto next_end = [&](int e) {
-        if (lz_uniform || !use_i8gemm || !trsm_route) return min(nblk_all, e + lz_group);
+        if (lz_forced || !use_i8gemm || !trsm_route) return min(nblk_all, e + lz_group);
         if (e < nblk_all / 2) return max(1, nblk_all / 2);
         const int tail_start = nblk_all - max(1, nblk_all / 8);
         return e < tail_start ? tail_start : nblk_all;
@@ -812,13 +865,18 @@ int gpirt_b200_sampler::launch_deferred_solves() {
     const int what = deferred;
     deferred = 0;
     if (what == 1) {
+        // on the factorisation's bulk stream (idle now, same top priority as the ESS on the main stream: on the trailing
+        // stream, one notch lower, the first kernel of the pass did not get an SM before the ESS had dispatched all of its
+        // CTAs — 0.37 ms into the sweep on 4 GPUs)
+        cudaStream_t st_tail = lookahead.aux ? lookahead.aux : st_trsm;
         GP_CUDA(cudaEventRecord(ev_linv, stream));
-        GP_CUDA(cudaStreamWaitEvent(st_trsm, ev_linv, 0));
-        Seg sg = tic_on(GPIRT_B200_T_TRSM, st_trsm);
-        GP_TRY(trsm_bwd(st_trsm, true));
-        toc_on(sg, st_trsm);
-        GP_CUDA(cudaEventRecord(ev_solve, st_trsm));
+        GP_CUDA(cudaStreamWaitEvent(st_tail, ev_linv, 0));
+        Seg sg = tic_on(GPIRT_B200_T_TRSM, st_tail);
+        GP_TRY(trsm_bwd(st_tail, true));
+        toc_on(sg, st_tail);
+        GP_CUDA(cudaEventRecord(ev_solve, st_tail));
         local_solve_ready = true;
+        tail_beside_ess = true;
     } else if (what == 2) {
         cudaStream_t st_solve = (pipe_mask & 4) ? st_lz : stream;
         GP_CUDA(cudaEventRecord(ev_linv, stream));
@@ -836,7 +894,7 @@ int gpirt_b200_sampler::sweep_eager(uint32_t t, int accumulate) {
     const bool can_pipe = pipeline && ceil_div(n, CHOL_NB) > 2;   // the look-ahead factorisation needs > 2 panels
     if (deferred) GP_TRY(launch_deferred_solves());
     if (can_pipe && nu_ready && nu_sweep == t) GP_TRY(ess_only(t));
-    else GP_TRY(step_draw_f(t));
+    else { tail_beside_ess = false; GP_TRY(step_draw_f(t)); }
     nu_ready = false;
     GP_TRY(step_draw_fstar(t, accumulate));
     GP_TRY(step_draw_theta(t));
@@ -920,6 +978,8 @@ void gpirt_b200_sampler::destroy() {
     if (lookahead.aux) { cudaStreamSynchronize(lookahead.aux); cudaStreamDestroy(lookahead.aux); lookahead.aux = nullptr; }
     for (cudaStream_t* q : {&st_beta, &st_lz, &st_trsm}) if (*q) { cudaStreamSynchronize(*q); cudaStreamDestroy(*q); *q = nullptr; }
     for (cudaEvent_t* e : {&ev_theta, &ev_z, &ev_beta, &ev_lz, &ev_linv, &ev_solve, &ev_fwd}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    dump_stamps();
+    if (d_stamps) { cudaFree(d_stamps); d_stamps = nullptr; }
     if (trace_file) { fclose(trace_file); trace_file = nullptr; }
     if (trace_ref) { cudaEventDestroy(trace_ref); trace_ref = nullptr; }
     comm_destroy(comm);
@@ -1350,9 +1410,11 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int n_slots = sample_iterations / thin + 1;         // slot 0 = initial values, slot k = sampling iteration k * thin
     const size_t nm = (size_t)n * m;
-    if (keep_f && !getenv("GPIRT_NO_HUGEPAGE_HINT")) {
-        // the caller's f array is fresh pageable memory: ask for transparent huge pages on its interior so that the
-        // first-touch faults of the draw stores are 2 MiB each instead of 4 KiB (advisory; ignored where THP is off)
+    if (keep_f && getenv("GPIRT_HUGEPAGE_HINT")) {
+        // the caller's f array is fresh pageable memory: optionally ask for transparent huge pages on its interior so that
+        // the first-touch faults of the draw stores are 2 MiB each instead of 4 KiB.  Off by default: with THP defrag set
+        // to "madvise" (this pool's hosts) a hinted fault compacts memory synchronously, and the stores were measured
+        // anywhere between 23 and 41 sweeps/s with the hint against a steady 43 without it.
         const uintptr_t a = ((uintptr_t)f_out + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
         const uintptr_t b = ((uintptr_t)f_out + (size_t)n_slots * nm * sizeof(double)) & ~(((uintptr_t)2 << 20) - 1);
         if (b > a) madvise((void*)a, b - a, MADV_HUGEPAGE);
