@@ -13,7 +13,7 @@
 // K 2^-51 amax_i bmax_j — the same order as the K 2^-53 sum|a||b| bound of an FP64 dot product when rows are not badly
 // scaled, which is the case for L (rows of unit norm), Z (normal draws), S^-1 K* and f.
 //
-// Kernel: persistent, one CTA per SM, 128 x 64 output tile.  A stage of the mbarrier ring holds all 8 digit planes of a
+// Kernel: persistent (one CTA per SM) or one tile per CTA, 128 x 64 output tile, CTAs in clusters of 2 that share the A slab.  A stage of the mbarrier ring holds all 8 digit planes of a
 // 128 x KB slab of A and a 64 x KB slab of B (KB = 64 bytes, SWIZZLE_64B, TMA-loaded); from it the elected thread issues
 // all 36 plane-pair MMAs (M = 128, N = 64, K = 32), each into the TMEM accumulator of its level l — 8 levels x 64
 // columns = the whole 512-column tensor memory.  Operand bytes are therefore read from L2 ONCE per stage, not once per
