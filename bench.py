@@ -496,7 +496,11 @@ def main():
     # ------------------------------------------------------------------ end-to-end through the public call (host buffers)
     if not args.no_e2e:
         from gpirt_b200 import ResponseMatrix
-        Ke = min(K, 12)   # f draws are n*m*8 bytes per stored sweep on the host; bound the host allocation
+        # f draws are n*m*8 bytes per stored sweep on the host: 30 sampling iterations of the local item block (10 GB at C3 on
+        # one GPU) amortise the fixed cost of a call (create 35 ms, first eager sweeps) the way a real run does; bounded
+        # by the host allocation, independent of --steps
+        per_slot = n * m_loc * 8
+        Ke = int(max(4, min(30, (12 << 30) // max(per_slot, 1))))
         yrm = ResponseMatrix(y_loc)
         common = dict(beta_prior_means=data["pm"][:, j0:j1], beta_prior_sds=data["psd"][:, j0:j1],
                       beta_proposal_sds=data["pstep"][:, j0:j1], theta_init=data["theta_init"], seed=synthetic.SEED,

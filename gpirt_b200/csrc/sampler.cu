@@ -1002,7 +1002,29 @@ namespace {
 struct Bounce {
     double* buf[2] = {nullptr, nullptr};
     size_t cap = 0;
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev[2];   // one event per DMA piece, per buffer
+    // small pinned staging of a call (theta | beta of a slot, twice; status words + agreement ring): kept across calls like
+    // the bounce buffers, so that a call neither pins nor unpins host memory (cudaFreeHost synchronises the device)
+    double* small[2] = {nullptr, nullptr};
+    size_t small_cap = 0;
+    int* poll = nullptr;
+    static constexpr size_t POLL_BYTES = 8 * sizeof(int) + 8 * sizeof(double);
+    int ensure_small(size_t count) {
+        if (!poll && cudaHostAlloc((void**)&poll, POLL_BYTES, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); poll = nullptr; return GPIRT_B200_ERR_NOMEM; }
+        if (count <= small_cap) return GPIRT_B200_OK;
+        for (auto& p : small) { if (p) cudaFreeHost(p); p = nullptr; }
+        small_cap = 0;
+        for (auto& p : small)
+            if (cudaHostAlloc((void**)&p, count * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return GPIRT_B200_ERR_NOMEM; }
+        small_cap = count;
+        return GPIRT_B200_OK;
+    }
+    void release() {
+        for (auto& p : buf) { if (p) cudaFreeHost(p); p = nullptr; }
+        for (auto& p : small) { if (p) cudaFreeHost(p); p = nullptr; }
+        if (poll) { cudaFreeHost(poll); poll = nullptr; }
+        cap = small_cap = 0;
+    }
     ~Bounce() { for (auto p : buf) if (p) cudaFreeHost(p); }
     int ensure(size_t count) {
         if (count <= cap) return GPIRT_B200_OK;
@@ -1018,7 +1040,7 @@ struct Bounce {
     }
 };
 Bounce g_bounce;        // process-wide, reused across calls (2 x n*m*8 bytes of pinned memory once f draws are stored)
-std::mutex g_bounce_mu; // one gpirt_b200_mcmc call at a time drains through it (concurrent calls take turns per slice)
+std::mutex g_bounce_mu; // held by a gpirt_b200_mcmc call for its whole duration (concurrent calls in one process take turns)
 
 int host_threads_for_copy() {
     const char* e = getenv("GPIRT_COPY_THREADS");
@@ -1029,45 +1051,75 @@ int host_threads_for_copy() {
     return t < 1 ? 1 : (t > 32 ? 32 : t);
 }
 
-// dst (pageable host) <- src (device), count doubles, via bounce buffer `b` on `stream`
-int chunked_d2h(double* dst, const double* src, size_t count, int b, cudaStream_t stream) {
-    std::lock_guard<std::mutex> lock(g_bounce_mu);
-    const size_t chunk = (size_t)4 << 20;   // 4 Mi doubles = 32 MiB
-    const int nchunks = (int)((count + chunk - 1) / chunk);
+// dst (pageable host) <- src (device), count doubles, via bounce buffer `b` on `stream`, in two phases so that the DMA of
+// the NEXT slice (other buffer) can be enqueued before the copy threads start on this one:
+//   bounce_issue   enqueues the DMA pieces and one event per piece
+//   bounce_finish  copy threads pick the pieces up as they land
+// Pieces are 4 MiB and start on 2 MiB boundaries of the DESTINATION: a slice lands in ~80 pieces, so the copy of the last
+// piece — the only part that cannot overlap the DMA — is 4 MiB by one thread (with 32 MiB pieces one thread spent 8-20 ms
+// on the last one after the DMA had finished: first-touch copies run at 1.5 GB/s per thread on 4 KiB pages, ~4 GB/s on
+// huge pages; tools/host_store_probe.cpp), and a huge page of the destination is first touched by exactly one thread.
+// The caller holds g_bounce_mu.
+struct BounceXfer {
+    std::vector<size_t> cut;   // piece boundaries in doubles
+    double* dst = nullptr;
+    bool staged = false;       // false: no pinned memory, the copy was done by the driver in bounce_issue
+};
+int bounce_issue(double* dst, const double* src, size_t count, int b, cudaStream_t stream, BounceXfer& x) {
+    x.dst = dst; x.cut.clear(); x.staged = false;
     if (g_bounce.ensure(count) != GPIRT_B200_OK) {   // no pinned memory: plain (driver-staged) copy
         GP_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream));
         GP_CUDA(cudaStreamSynchronize(stream));
         return GPIRT_B200_OK;
     }
-    while ((int)g_bounce.ev.size() < nchunks) {
+    const size_t piece = (size_t)4 << 20, huge = (size_t)2 << 20;   // bytes
+    const uintptr_t d0 = (uintptr_t)dst, d1 = d0 + count * sizeof(double);
+    x.cut.push_back(0);
+    uintptr_t next = ((d0 + huge) & ~(uintptr_t)(huge - 1));        // first 2 MiB boundary after the start
+    if (next - d0 < huge / 2) next += piece - huge;                   // no tiny first piece
+    while (next < d1) { x.cut.push_back((next - d0) / sizeof(double)); next += piece; }
+    x.cut.push_back(count);
+    const int npieces = (int)x.cut.size() - 1;
+    while ((int)g_bounce.ev[b].size() < npieces) {
         cudaEvent_t e;
         GP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        g_bounce.ev.push_back(e);
+        g_bounce.ev[b].push_back(e);
     }
     double* bb = g_bounce.buf[b];
-    for (int c = 0; c < nchunks; ++c) {
-        const size_t off = (size_t)c * chunk, len = std::min(chunk, count - off);
-        GP_CUDA(cudaMemcpyAsync(bb + off, src + off, len * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        GP_CUDA(cudaEventRecord(g_bounce.ev[c], stream));
+    for (int c = 0; c < npieces; ++c) {
+        GP_CUDA(cudaMemcpyAsync(bb + x.cut[c], src + x.cut[c], (x.cut[c + 1] - x.cut[c]) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA(cudaEventRecord(g_bounce.ev[b][c], stream));
     }
-    const int T = std::min(host_threads_for_copy(), nchunks);
+    x.staged = true;
+    return GPIRT_B200_OK;
+}
+int bounce_finish(int b, BounceXfer& x) {
+    if (!x.staged) return GPIRT_B200_OK;
+    const int npieces = (int)x.cut.size() - 1;
+    const double* bb = g_bounce.buf[b];
+    const int T = std::min(host_threads_for_copy(), npieces);
     std::atomic<int> next{0};
     std::atomic<int> failed{0};
     auto work = [&]() {
         for (;;) {
             const int c = next.fetch_add(1);
-            if (c >= nchunks) break;
-            if (cudaEventSynchronize(g_bounce.ev[c]) != cudaSuccess) { failed = 1; break; }
-            const size_t off = (size_t)c * chunk, len = std::min(chunk, count - off);
-            std::memcpy(dst + off, bb + off, len * sizeof(double));
+            if (c >= npieces) break;
+            if (cudaEventSynchronize(g_bounce.ev[b][c]) != cudaSuccess) { failed = 1; break; }
+            std::memcpy(x.dst + x.cut[c], bb + x.cut[c], (x.cut[c + 1] - x.cut[c]) * sizeof(double));
         }
     };
     std::vector<std::thread> th;
     for (int t = 1; t < T; ++t) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
+    x.staged = false;
     if (failed) { set_last_error("device-to-host copy of a draw slice failed"); return GPIRT_B200_ERR_CUDA; }
     return GPIRT_B200_OK;
+}
+int chunked_d2h(double* dst, const double* src, size_t count, int b, cudaStream_t stream) {
+    BounceXfer x;
+    GP_TRY(bounce_issue(dst, src, count, b, stream, x));
+    return bounce_finish(b, x);
 }
 }  // namespace
 
@@ -1096,8 +1148,7 @@ int gpirt_b200_release_memory(void) {
     GP_TRY(comm_shutdown());
     {
         std::lock_guard<std::mutex> lock(g_bounce_mu);
-        for (auto& p : g_bounce.buf) { if (p) cudaFreeHost(p); p = nullptr; }
-        g_bounce.cap = 0;
+        g_bounce.release();
     }
     int dev = 0;
     GP_CUDA(cudaGetDevice(&dev));
@@ -1282,7 +1333,9 @@ struct StoreWorker {
     bool quit = false;
     int rc = GPIRT_B200_OK;            // first failure of a drain
     std::string error;
-    std::function<int(int)> drain;     // runs on the worker thread
+    std::function<int(int)> issue;     // enqueue the device-to-host transfers of a slot        (both run on the worker thread)
+    std::function<int(int)> finish;    // land them in the caller's arrays
+    int issued = -1;                   // last slot whose transfers are enqueued
     std::thread th;
     int device = 0;
     double busy_s = 0.0;
@@ -1305,7 +1358,16 @@ struct StoreWorker {
                     r = rc;
                 }
                 if (r == GPIRT_B200_OK) {              // after a failure the remaining jobs are dropped
-                    r = drain(slot);
+                    if (issued != slot) { r = issue(slot); issued = slot; }
+                    if (r == GPIRT_B200_OK) {          // the next slot's DMA (other buffers) runs under this slot's host copies
+                        int nxt = -1;
+                        {
+                            std::lock_guard<std::mutex> lk(mu);
+                            if (!jobs.empty()) nxt = jobs.front();
+                        }
+                        if (nxt >= 0 && (nxt & 1) != (slot & 1)) { r = issue(nxt); issued = nxt; }
+                    }
+                    if (r == GPIRT_B200_OK) r = finish(slot);
                     if (r != GPIRT_B200_OK) {
                         std::lock_guard<std::mutex> lk(mu);
                         rc = r;
@@ -1390,6 +1452,17 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     g_last_degenerate_theta = 0;
     double t_a = now();
+    struct ExitTrace {   // first local: destroyed last
+        bool on; double t_enter; double t_body_end = 0.0;
+        ~ExitTrace() {
+            if (!on) return;
+            timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+            const double t = ts.tv_sec + 1e-9 * ts.tv_nsec;
+            fprintf(stderr, "gpirt_b200_mcmc: total %.3fs in the call, %.3fs after the body\n", t - t_enter, t_body_end > 0.0 ? t - t_body_end : 0.0);
+        }
+    } exit_trace{trace, t_a};
+    // the pinned bounce buffers are process-wide: a call that moves f through them owns them until it returns
+    std::unique_lock<std::mutex> bounce_lock(g_bounce_mu);
     gpirt_b200_sampler* s = nullptr;
     GP_TRY(gpirt_b200_sampler_create(&s, y, n, m, theta_init, pm, psd, pstep, opts));
     s->timing = false;
@@ -1399,36 +1472,50 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     struct Guard {
         gpirt_b200_sampler* s; cudaStream_t copy; cudaEvent_t ev[2]; double* snap_f[2]; double* snap_small[2];
         double *f_mean, *f_m2, *agree_dev; int* h_poll; StoreWorker* worker;
+        double* h_small[2]; cudaEvent_t ev_small[2];
+        bool trace = false;
         ~Guard() {
+            auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+            const double t0 = now();
             if (worker) { worker->stop(); delete worker; }   // before anything it uses goes away
             if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
+            const double t1 = now();
+            for (int i = 0; i < 2; ++i) if (ev_small[i]) cudaEventDestroy(ev_small[i]);   // h_small / h_poll belong to g_bounce
             for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); pool_free(snap_f[i], s->stream); pool_free(snap_small[i], s->stream); }
             pool_free(f_mean, s->stream); pool_free(f_m2, s->stream); pool_free(agree_dev, s->stream);
-            if (h_poll) cudaFreeHost(h_poll);
+            const double t2 = now();
             gpirt_b200_sampler_destroy(s);
+            if (trace) fprintf(stderr, "gpirt_b200_mcmc: teardown worker/copy stream %.3fs, host + pool frees %.3fs, sampler %.3fs\n", t1 - t0, t2 - t1, now() - t2);
         }
-    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, nullptr};
+    } gd{s, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, nullptr,
+         {nullptr, nullptr}, {nullptr, nullptr}};
+    gd.trace = trace;
     const int n_slots = sample_iterations / thin + 1;         // slot 0 = initial values, slot k = sampling iteration k * thin
     const size_t nm = (size_t)n * m;
-    if (keep_f && getenv("GPIRT_HUGEPAGE_HINT")) {
-        // the caller's f array is fresh pageable memory: optionally ask for transparent huge pages on its interior so that
-        // the first-touch faults of the draw stores are 2 MiB each instead of 4 KiB.  Off by default: with THP defrag set
-        // to "madvise" (this pool's hosts) a hinted fault compacts memory synchronously, and the stores were measured
-        // anywhere between 23 and 41 sweeps/s with the hint against a steady 43 without it.
+    if (keep_f && !getenv("GPIRT_NO_HUGEPAGE_HINT")) {
+        // the caller's f array is fresh pageable memory: ask for transparent huge pages on its interior so that the
+        // first-touch faults of the draw stores are 2 MiB each instead of 4 KiB (advisory; ignored where THP is off).
+        // On this pool's hosts 12 threads copy a 328 MB slice into fresh memory in 19 ms on 4 KiB pages and in 10 ms on
+        // huge pages (tools/host_store_probe.cpp); numpy gives its large arrays the same hint, R's allocator does not.
         const uintptr_t a = ((uintptr_t)f_out + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
         const uintptr_t b = ((uintptr_t)f_out + (size_t)n_slots * nm * sizeof(double)) & ~(((uintptr_t)2 << 20) - 1);
         if (b > a) madvise((void*)a, b - a, MADV_HUGEPAGE);
     }
-    std::vector<double> small((size_t)n + 2 * (size_t)m);
+    const size_t n_small = (size_t)n + 2 * (size_t)m;     // theta | beta of one slot
     GP_CUDA(cudaStreamCreateWithFlags(&gd.copy, cudaStreamNonBlocking));
-    GP_CUDA(cudaHostAlloc((void**)&gd.h_poll, 8 * sizeof(int) + 8 * sizeof(double), cudaHostAllocDefault));
-    std::memset(gd.h_poll, 0, 8 * sizeof(int) + 8 * sizeof(double));   // [0..3] status words polled by this thread, [4..7] by the
+    if (g_bounce.ensure_small(n_small) != GPIRT_B200_OK) { set_last_error("pinned host staging could not be allocated"); return GPIRT_B200_ERR_NOMEM; }
+    for (int i = 0; i < 2; ++i) {
+        gd.h_small[i] = g_bounce.small[i];
+        GP_CUDA(cudaEventCreateWithFlags(&gd.ev_small[i], cudaEventDisableTiming));
+    }
+    gd.h_poll = g_bounce.poll;
+    std::memset(gd.h_poll, 0, Bounce::POLL_BYTES);   // [0..3] status words polled by this thread, [4..7] by the
     double* h_ring = reinterpret_cast<double*>(gd.h_poll + 8);         // storage worker, then a ring of 8 agreed stop flags
     volatile int* w_poll = gd.h_poll + 4;
     int agree_count = 0;
     for (int i = 0; i < 2; ++i) {
         GP_CUDA(cudaEventCreateWithFlags(&gd.ev[i], cudaEventDisableTiming));
-        GP_TRY(pool_alloc((void**)&gd.snap_small[i], small.size() * sizeof(double), s->stream));
+        GP_TRY(pool_alloc((void**)&gd.snap_small[i], n_small * sizeof(double), s->stream));
         if (keep_f) GP_TRY(pool_alloc((void**)&gd.snap_f[i], nm * sizeof(double), s->stream));
     }
     if (summarise_f) {
@@ -1457,24 +1544,43 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     gd.worker = new StoreWorker();
     StoreWorker& worker = *gd.worker;
     GP_CUDA(cudaGetDevice(&worker.device));
-    worker.drain = [&, n_slots](int slot) -> int {   // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
-        const double ts0 = now();
+    // issue(slot): the copy stream waits for the snapshot and gets every device-to-host transfer of the slot (status words,
+    // theta | beta into pinned staging, f in pieces into the pinned bounce buffer); finish(slot): the host copies.
+    // The worker issues slot k+1 (other snapshot / bounce / staging buffers) before it finishes slot k, so the PCIe transfer
+    // of one slice runs under the host copies of the previous one.
+    BounceXfer xfer[2];
+    worker.issue = [&](int slot) -> int {            // theta_draws.row(slot), beta_draws.slice(slot), f_draws.slice(slot)
         const int b = slot & 1;
         GP_CUDA(cudaStreamWaitEvent(gd.copy, gd.ev[b], 0));
         GP_CUDA(cudaMemcpyAsync((void*)w_poll, s->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, gd.copy));
-        GP_CUDA(cudaMemcpyAsync(small.data(), gd.snap_small[b], small.size() * sizeof(double), cudaMemcpyDeviceToHost, gd.copy));
-        if (keep_f) GP_TRY(chunked_d2h(f_out + (size_t)slot * nm, gd.snap_f[b], nm, b, gd.copy));
-        GP_CUDA(cudaStreamSynchronize(gd.copy));
+        GP_CUDA(cudaMemcpyAsync(gd.h_small[b], gd.snap_small[b], n_small * sizeof(double), cudaMemcpyDeviceToHost, gd.copy));
+        GP_CUDA(cudaEventRecord(gd.ev_small[b], gd.copy));
+        if (keep_f) GP_TRY(bounce_issue(f_out + (size_t)slot * nm, gd.snap_f[b], nm, b, gd.copy, xfer[b]));
+        return GPIRT_B200_OK;
+    };
+    worker.finish = [&, n_slots](int slot) -> int {
+        const double ts0 = now();
+        const int b = slot & 1;
+        if (keep_f) GP_TRY(bounce_finish(b, xfer[b]));
+        GP_CUDA(cudaEventSynchronize(gd.ev_small[b]));
+        const double* small = gd.h_small[b];
         for (int64_t i = 0; i < n; ++i) theta_out[(size_t)i * n_slots + slot] = small[i];
-        std::memcpy(beta_out + (size_t)slot * 2 * m, small.data() + n, 2 * (size_t)m * sizeof(double));
+        std::memcpy(beta_out + (size_t)slot * 2 * m, small + n, 2 * (size_t)m * sizeof(double));
         worker.busy_s += now() - ts0;
         return GPIRT_B200_OK;
     };
     worker.start();
     struct WorkerStop {   // declared after everything the drain closure refers to: the worker is joined before any of it dies
         StoreWorker* w;
-        ~WorkerStop() { w->stop(); }
-    } worker_stop{gd.worker};
+        bool trace;
+        ~WorkerStop() {
+            timespec a, b;
+            clock_gettime(CLOCK_MONOTONIC, &a);
+            w->stop();
+            clock_gettime(CLOCK_MONOTONIC, &b);
+            if (trace) fprintf(stderr, "gpirt_b200_mcmc: storage thread joined in %.3fs\n", (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec));
+        }
+    } worker_stop{gd.worker, trace};
     // Stopping early (interrupt from the progress callback, failed Cholesky / ESS seen in the polled status words, a failed
     // store) must be a COMMON decision when items are sharded: a rank that returned alone would leave its peers blocked in
     // the next sweep's collectives.  Every rank therefore enqueues, every 8th iteration, a one-word all-reduce of its local
@@ -1577,6 +1683,7 @@ int gpirt_b200_mcmc(const double* y, int64_t n, int64_t m, const double* theta_i
     if (trace)
         fprintf(stderr, "gpirt_b200_mcmc: create %.3fs, copy buffers %.3fs, init draws %.3fs, %d sweeps + stores %.3fs (stores %.3fs)\n",
                 t_b - t_a, t_c - t_b, t_d - t_c, total, now() - t_d, t_store);
+    exit_trace.t_body_end = now();
     return GPIRT_B200_OK;
 }
 
