@@ -39,8 +39,10 @@ typedef struct gpirt_b200_opts {
     int32_t fstar_mode;   /* 0: mean_j = (S^-1 K*)^T f_j (two n x 1001 triangular solves per sweep);
                              1: literal per-item alpha_j = L^-T L^-1 f_j (draw-fstar.cpp:3-8,24) */
     int32_t skip_f_draws; /* 1: do not store f draws (f_out may be NULL); reference behaviour is 0 */
-    int32_t use_graph;    /* 0 (default): small problems (un-pipelined sweep, n <= 256) replay each sweep as one CUDA graph launch;
-                             -1: never (every kernel launched individually); draws are identical either way */
+    int32_t use_graph;    /* 0 (default): with the per-step timers off (always in gpirt_b200_mcmc) every sweep after the first is
+                             replayed as ONE CUDA graph launch — for n > 256 the pipelined sweep with its side streams
+                             forked and joined inside the graph, NCCL exchanges included; -1: never (every kernel
+                             launched individually); draws are bit-identical either way */
     /* item sharding across GPUs (one process per GPU).  world_size <= 1: single GPU, fields ignored. */
     int32_t rank, world_size;
     int64_t m_global;     /* total items over all ranks */
