@@ -467,6 +467,12 @@ def main():
                              "note": "potrf_lower_rl: k_diag128 + k_panel_update chain with look-ahead bulk updates on gemm_f64_kernel"},
                 "per_step_ms": {k: v[0] / K for k, v in timers.items() if v[1]},
                 "per_step_ms_isolated": {k: v[0] / Ki for k, v in t_iso.items() if v[1]}}
+    try:   # the factorisation alone, eager and as the product runs it (replayed as a CUDA graph): K build + chain
+        chol_eager, chol_graph = s.time_factorisation(10, False), s.time_factorisation(10, True)
+        roofline["cholesky"].update({"ms_alone_eager_incl_k_build": chol_eager, "ms_alone_graph_replay_incl_k_build": chol_graph,
+                                     "frac_of_fp64_tensor_peak_graph_replay": n ** 3 / 3.0 / chol_graph * 1e-9 / dmma})
+    except Exception as exc:   # measurement extra only
+        roofline["cholesky"]["graph_replay_error"] = str(exc)
     s.close()
 
     line = {"metric": "gibbs_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": max(3, W),

@@ -15,7 +15,7 @@ EXPORTS = [
     "gpirt_b200_release_memory",
     "gpirt_b200_nccl_unique_id", "gpirt_b200_sampler_create", "gpirt_b200_sampler_init_draws",
     "gpirt_b200_sampler_sweep", "gpirt_b200_sampler_step", "gpirt_b200_sampler_get", "gpirt_b200_sampler_set",
-    "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_set_pipeline",
+    "gpirt_b200_sampler_timings", "gpirt_b200_sampler_set_timing", "gpirt_b200_sampler_set_pipeline", "gpirt_b200_sampler_time_factorisation",
     "gpirt_b200_sampler_launches", "gpirt_b200_sampler_uses",
     "gpirt_b200_sampler_destroy", "gpirt_b200_se_cov", "gpirt_b200_chol_lower", "gpirt_b200_dgemm", "gpirt_b200_dgemm_i8",
     "gpirt_b200_trsm_lower", "gpirt_b200_ll_bar", "gpirt_b200_fp64_peak_tflops", "gpirt_b200_int8_peak_tops", "gpirt_b200_int8_peak_tops_random", "gpirt_b200_rng_probe", "gpirt_b200_response_matrix", "gpirt_b200_theta_diagnostics",
@@ -74,6 +74,7 @@ def load():
     L.gpirt_b200_sampler_timings.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int64), C.c_int]
     L.gpirt_b200_sampler_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.gpirt_b200_sampler_set_pipeline.argtypes = [C.c_void_p, C.c_int]
+    L.gpirt_b200_sampler_time_factorisation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.gpirt_b200_sampler_launches.argtypes = [C.c_void_p]
     L.gpirt_b200_sampler_launches.restype = C.c_int64
     L.gpirt_b200_sampler_uses.argtypes = [C.c_void_p, C.c_int]

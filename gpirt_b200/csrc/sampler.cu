@@ -1297,6 +1297,58 @@ int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled) {
     return GPIRT_B200_OK;
 }
 
+// Time of K(theta, theta) + 0.001 I and its factorisation alone (no other work on the GPU), per repetition, either as the
+// eager launch sequence or replayed as a CUDA graph of the same sequence (the way a sweep runs it inside gpirt_b200_mcmc).
+// Measurement facility for bench.py; the factor is left in place (same theta: same L).
+int gpirt_b200_sampler_time_factorisation(gpirt_b200_sampler* s, int reps, int as_graph, float* ms_per_rep) {
+    if (!s || reps <= 0 || !ms_per_rep) return GPIRT_B200_ERR_ARG;
+    GP_TRY(s->check_status());                              // drains every stream of the sampler
+    s->nu_ready = false;
+    s->deferred = 0;
+    s->solve_ready = s->local_solve_ready = false;
+    const bool timing_was = s->timing;
+    s->timing = false;
+    struct Restore { gpirt_b200_sampler* s; bool t; ~Restore() { s->timing = t; } } restore{s, timing_was};
+    auto once = [&]() -> int {
+        GP_TRY(launch_se_cov(s->stream, s->theta, s->n, s->theta, s->n, 0.001, true, s->L, s->ldn));
+        return potrf_lower_rl(s->stream, s->L, s->ldn, s->n, s->Dinv, s->ldn, s->status, s->chol_flags, &s->lookahead);
+    };
+    GP_TRY(once());                                         // warm (lazy attribute set-up, events of the look-ahead)
+    GP_CUDA(cudaStreamSynchronize(s->stream));
+    cudaGraphExec_t exec = nullptr;
+    if (as_graph) {
+        cudaGraph_t graph = nullptr;
+        const int64_t counted = g_launch_count;
+        GP_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = once();
+        const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        g_launch_count = counted;
+        if (rc != GPIRT_B200_OK || e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); set_last_error("the factorisation could not be captured"); return GPIRT_B200_ERR_CUDA; }
+        const cudaError_t ei = cudaGraphInstantiateWithFlags(&exec, graph, cudaGraphInstantiateFlagUseNodePriority);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { cudaGetLastError(); set_last_error("the factorisation graph could not be instantiated"); return GPIRT_B200_ERR_CUDA; }
+        GP_CUDA(cudaGraphLaunch(exec, s->stream));          // one untimed replay
+        GP_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    cudaEvent_t e0, e1;
+    GP_CUDA(cudaEventCreate(&e0)); GP_CUDA(cudaEventCreate(&e1));
+    int rc = GPIRT_B200_OK;
+    cudaEventRecord(e0, s->stream);
+    for (int r = 0; r < reps && rc == GPIRT_B200_OK; ++r) {
+        if (exec) { if (cudaGraphLaunch(exec, s->stream) != cudaSuccess) rc = GPIRT_B200_ERR_CUDA; }
+        else rc = once();
+    }
+    cudaEventRecord(e1, s->stream);
+    const cudaError_t es = cudaStreamSynchronize(s->stream);
+    float t = 0.f;
+    if (es == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (rc != GPIRT_B200_OK || es != cudaSuccess) { cudaGetLastError(); set_last_error("timing the factorisation failed"); return GPIRT_B200_ERR_CUDA; }
+    *ms_per_rep = t / reps;
+    return s->check_status();
+}
+
 int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s) { return s ? g_launch_count - s->launches_at_create : 0; }
 int gpirt_b200_sampler_uses(gpirt_b200_sampler* s, int feature) {
     if (!s) return -1;

@@ -152,6 +152,12 @@ class Sampler:
     def set_pipeline(self, on):
         _lib.check(_lib.load().gpirt_b200_sampler_set_pipeline(self.h, int(on)))
 
+    def time_factorisation(self, reps=10, as_graph=False):
+        """ms per K(theta) build + Cholesky alone on the GPU, eager or replayed as a CUDA graph"""
+        ms = C.c_float(0)
+        _lib.check(_lib.load().gpirt_b200_sampler_time_factorisation(self.h, int(reps), int(as_graph), C.byref(ms)))
+        return ms.value
+
     def timings(self, reset=False):
         ms = np.zeros(len(_lib.TIMER_NAMES))
         calls = np.zeros(len(_lib.TIMER_NAMES), dtype=np.int64)

@@ -140,6 +140,9 @@ int gpirt_b200_sampler_set_timing(gpirt_b200_sampler* s, int enabled); /* per-st
 /* sweep pipelining on (default) / off: on, the Cholesky chain of a sweep overlaps its beta step and the next sweep's
  * Z fill and L Z product (identical draws either way; off gives un-overlapped per-kernel timings) */
 int gpirt_b200_sampler_set_pipeline(gpirt_b200_sampler* s, int enabled);
+/* measurement: milliseconds per repetition of K(theta,theta) + 0.001 I and its Cholesky factorisation alone on the GPU
+ * (gpirtMCMC.cpp:76-78), as the eager launch sequence (as_graph = 0) or replayed as a CUDA graph of it (as_graph = 1) */
+int gpirt_b200_sampler_time_factorisation(gpirt_b200_sampler* s, int reps, int as_graph, float* ms_per_rep);
 int64_t gpirt_b200_sampler_launches(gpirt_b200_sampler* s); /* kernels launched by this sampler so far */
 /* which code path this sampler selected (bench.py picks the roofline denominator by it, the parity tests assert it):
  * feature 0 = int8 theta contraction (1/0), 1 = fixed-point (int8) L Z / f* / K*-solve products (1/0),
