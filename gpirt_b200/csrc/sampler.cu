@@ -232,7 +232,8 @@ struct gpirt_b200_sampler {
         k.sweep_dev = capturing ? d_sweep : nullptr;
         return k;
     }
-    // ---- CUDA graph of the un-pipelined sweep (small n: the sweep is ~40 short kernels and pure launch latency) ----
+    // ---- CUDA graph of a sweep (small n: ~20 short kernels, pure launch latency; n > 256: the pipelined sweep, whose
+    // Cholesky chain takes ~15 host API calls per panel — with items sharded the host is the limit otherwise) ----
     bool graph_enabled = true, capturing = false, warmed = false;
     uint32_t capture_base = 0;
     uint32_t* d_sweep = nullptr;          // device copy of the sweep counter read by the captured kernels
@@ -904,10 +905,12 @@ int gpirt_b200_sampler::sweep_eager(uint32_t t, int accumulate) {
     return GPIRT_B200_OK;
 }
 
-// The un-pipelined sweep as one CUDA graph launch: captured once per value of `accumulate` from the very launch sequence
-// of sweep_eager (same kernels, same order, same draws: the sweep counter reaches the kernels through d_sweep, which
-// the first node of the graph bumps).  At n = 100 a sweep is ~40 kernels of a few microseconds each; the graph removes
-// the per-launch host cost and most of the gaps between dependent kernels.
+// A sweep as one CUDA graph launch: captured once per value of `accumulate` from the very launch sequence of sweep_eager
+// (same kernels, same order, same draws: the sweep counter reaches the kernels through d_sweep, which the first node of
+// the graph bumps).  At n = 100 a sweep is ~20 kernels of a few microseconds each; the graph removes the per-launch host
+// cost and most of the gaps between dependent kernels.  The pipelined sweep is captured with its side streams: they fork
+// from and join the capturing stream inside sweep_eager (launch_deferred_solves / rebuild_pipelined), every launch carries
+// its stream's priority as a launch attribute (GP_LAUNCH) and the graph is instantiated with per-node priorities.
 int gpirt_b200_sampler::sweep_graph(uint32_t t, int accumulate) {
     const int a = accumulate ? 1 : 0;
     if (!gexec[a]) {
